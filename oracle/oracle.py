@@ -1,0 +1,226 @@
+"""ctypes front-end of oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY.
+
+Each function mirrors the reference call it restates (file:line under /root/reference):
+  bpr_fit      <- cymf/bpr.pyx:117-171  (`BPR._fit_bpr`, num_threads=1)
+  als_half     <- cymf/wmf.pyx:136-174  (`WMF._als`)
+  glove_fit    <- cymf/glove.pyx:117-156 (`GloVe._fit_glove`)
+  evaluate     <- cymf/evaluator.pyx:57-139 (`Evaluator.evaluate`, unbiased=False)
+  rng_*        <- cymf/math.pyx:12-18 (`UniformGenerator`)
+plus the Python prologues of `fit()` (seeded init + one-time shuffle), which are host logic shared
+verbatim with the product (they are NumPy/sklearn calls in the reference too).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "cymf_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.check_call([cc, "-O2", "-std=c99", "-fPIC", "-shared", "-ffp-contract=off",
+                               src, "-o", _SO, "-lm"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.oracle_rng_new.restype = C.c_void_p
+        _lib.oracle_rng_new.argtypes = [C.c_uint32]
+        _lib.oracle_rng_free.argtypes = [C.c_void_p]
+        _lib.oracle_rng_fill_u32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        _lib.oracle_rng_fill_below.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int64]
+        _lib.oracle_bpr_fit.restype = C.c_int
+        _lib.oracle_bpr_fit.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_uint32,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.oracle_als_half.restype = C.c_int
+        _lib.oracle_als_half.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_double]
+        _lib.oracle_glove_fit.restype = C.c_int
+        _lib.oracle_glove_fit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                          C.c_double, C.c_double, C.c_double, C.c_void_p]
+        _lib.oracle_eval_candidates.restype = C.c_int64
+        _lib.oracle_eval_candidates.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p]
+        _lib.oracle_eval_rank.restype = C.c_int
+        _lib.oracle_eval_rank.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                          C.c_void_p]
+        for name in ("oracle_dcg_at_k", "oracle_recall_at_k", "oracle_ap_at_k"):
+            f = getattr(_lib, name)
+            f.restype = C.c_double
+            f.argtypes = [C.c_void_p, C.c_int64, C.c_int32]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+OPTIMIZERS = {"sgd": 0, "adagrad": 1, "adam": 2}
+
+
+class Rng:
+    """std::mt19937(seed) + uniform_int_distribution<long>(0, n-1) of libstdc++ >= 11."""
+
+    def __init__(self, seed=1234):
+        self._h = lib().oracle_rng_new(seed)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_rng_free(self._h)
+            self._h = None
+
+    def u32(self, count):
+        out = np.empty(count, np.uint32)
+        lib().oracle_rng_fill_u32(self._h, _p(out), count)
+        return out
+
+    def below(self, n, count):
+        out = np.empty(count, np.int32)
+        lib().oracle_rng_fill_below(self._h, n, _p(out), count)
+        return out
+
+
+def init_factors(U, I, K):
+    """`fit()` prologue, cymf/bpr.pyx:97-101 == cymf/wmf.pyx:88-92 (both factors absent)."""
+    np.random.seed(4321)
+    W = np.random.uniform(low=-0.1, high=0.1, size=(U, K)) / K
+    H = np.random.uniform(low=-0.1, high=0.1, size=(I, K)) / K
+    return W, H
+
+
+def bpr_prologue(X, K):
+    """cymf/bpr.pyx:81-104: CSR coercion, seeded init, one-time shuffle of the (user, positive) pairs."""
+    from sklearn import utils
+    X = X.tocsr().astype(np.float64)
+    W, H = init_factors(X.shape[0], X.shape[1], K)
+    users, positives = utils.shuffle(*(X.nonzero()))
+    return X, W, H, users.astype(np.int32), positives.astype(np.int32)
+
+
+def bpr_fit(W, H, users, positives, X, num_epochs, lr, wd, optimizer="sgd", seed=1234,
+            record=False, loss=False):
+    """In-place on W, H (float64 C-contiguous). Returns dict with optional negatives/applied/loss."""
+    assert W.dtype == np.float64 and H.dtype == np.float64 and W.flags.c_contiguous and H.flags.c_contiguous
+    X = X.tocsr()
+    X.sort_indices()
+    indptr = np.ascontiguousarray(X.indptr, np.int32)
+    indices = np.ascontiguousarray(X.indices, np.int32)
+    users = np.ascontiguousarray(users, np.int32)
+    positives = np.ascontiguousarray(positives, np.int32)
+    N = users.shape[0]
+    neg = np.empty(num_epochs * N, np.int32) if record else None
+    app = np.empty(num_epochs * N, np.uint8) if record else None
+    ls = np.empty(num_epochs, np.float64) if loss else None
+    rc = lib().oracle_bpr_fit(_p(W), _p(H), X.shape[0], X.shape[1], W.shape[1], _p(users), _p(positives), N,
+                              _p(indptr), _p(indices), num_epochs, lr, wd, OPTIMIZERS[optimizer], seed,
+                              _p(neg), _p(app), _p(ls))
+    if rc:
+        raise MemoryError("oracle_bpr_fit")
+    return {"negatives": neg, "applied": app, "loss": ls}
+
+
+def als_half(indptr, indices, X, Y, wd, weight):
+    """`WMF._als(indptr, indices, X, Y, num_threads)`: solves every row of X in place."""
+    assert X.dtype == np.float64 and Y.dtype == np.float64 and X.flags.c_contiguous and Y.flags.c_contiguous
+    indptr = np.ascontiguousarray(indptr, np.int64)
+    indices = np.ascontiguousarray(indices, np.int32)
+    rc = lib().oracle_als_half(_p(indptr), _p(indices), _p(X), _p(Y), X.shape[0], Y.shape[0], X.shape[1],
+                               wd, weight)
+    if rc:
+        raise MemoryError("oracle_als_half")
+
+
+def wmf_fit(X, K, wd, weight, num_epochs, W=None, H=None):
+    """`WMF.fit` (cymf/wmf.pyx:59-132) without evaluator."""
+    X = X.tocsr().astype(np.float64)
+    if W is None or H is None:
+        W, H = init_factors(X.shape[0], X.shape[1], K)
+    XT = X.T.tocsr()
+    for _ in range(num_epochs):
+        als_half(X.indptr, X.indices, W, H, wd, weight)
+        als_half(XT.indptr, XT.indices, H, W, wd, weight)
+    return W, H
+
+
+def glove_fit(central, context, counts, W, bw, H, bh, num_epochs, lr, x_max, alpha, loss=False):
+    """`GloVe._fit_glove` with caller-supplied arrays; in place on W, bw, H, bh."""
+    for a in (W, bw, H, bh):
+        assert a.dtype == np.float64 and a.flags.c_contiguous
+    central = np.ascontiguousarray(central, np.int32)
+    context = np.ascontiguousarray(context, np.int32)
+    counts = np.ascontiguousarray(counts, np.float64)
+    assert bw.shape[0] >= W.shape[0] and bh.shape[0] >= H.shape[0] or True
+    ls = np.empty(num_epochs, np.float64) if loss else None
+    rc = lib().oracle_glove_fit(_p(central), _p(context), _p(counts), central.shape[0], _p(W), _p(bw), _p(H), _p(bh),
+                                bw.shape[0], bh.shape[0], W.shape[1], num_epochs, lr, x_max, alpha, _p(ls))
+    if rc:
+        raise MemoryError("oracle_glove_fit")
+    return ls
+
+
+def eval_candidates(test, train, num_negatives=100, seed=1234):
+    """Candidate lists of `Evaluator.evaluate` (cymf/evaluator.pyx:95-111). Returns (cand_ptr, cand_items)."""
+    from scipy import sparse
+    test = sparse.csr_matrix(test)
+    allp = test.copy()
+    if train is not None:
+        allp = allp + sparse.csr_matrix(train)
+    allp = allp.tocsr()
+    allp.sort_indices()
+    U, I = test.shape
+    tip = np.ascontiguousarray(test.indptr, np.int32)
+    tix = np.ascontiguousarray(test.indices, np.int32)
+    aip = np.ascontiguousarray(allp.indptr, np.int32)
+    aix = np.ascontiguousarray(allp.indices, np.int32)
+    n_eval = int((np.diff(tip) > 0).sum())
+    cand_ptr = np.empty(U + 1, np.int64)
+    cand_items = np.empty(test.nnz + n_eval * num_negatives, np.int32)
+    n = lib().oracle_eval_candidates(U, I, _p(tip), _p(tix), _p(aip), _p(aix), num_negatives, seed,
+                                     _p(cand_ptr), _p(cand_items))
+    assert n == cand_items.shape[0]
+    return cand_ptr, cand_items
+
+
+def evaluate(W, H, test, train=None, k=5, num_negatives=100, seed=1234, metrics=("DCG", "Recall", "MAP"),
+             return_order=False):
+    """`Evaluator(test, train, metrics, k, num_negatives).evaluate(W, H, seed)` -> {"DCG@5": ...}."""
+    from scipy import sparse
+    test = sparse.csr_matrix(test)
+    W = np.ascontiguousarray(W, np.float64)
+    H = np.ascontiguousarray(H, np.float64)
+    cand_ptr, cand_items = eval_candidates(test, train, num_negatives, seed)
+    ks = np.ascontiguousarray([k] if isinstance(k, int) else list(k), np.int32)
+    out = np.zeros((ks.shape[0], 3), np.float64)
+    order = np.empty(cand_items.shape[0], np.int32) if return_order else None
+    tip = np.ascontiguousarray(test.indptr, np.int32)
+    rc = lib().oracle_eval_rank(_p(W), _p(H), test.shape[0], W.shape[1], _p(tip), _p(cand_ptr), _p(cand_items),
+                                _p(ks), ks.shape[0], _p(out), _p(order))
+    if rc:
+        raise MemoryError("oracle_eval_rank")
+    col = {"DCG": 0, "Recall": 1, "MAP": 2}
+    res = {f"{m}@{int(kk)}": float(out[q, col[m]]) for q, kk in enumerate(ks) for m in metrics}
+    if return_order:
+        return res, cand_ptr, cand_items, order
+    return res
+
+
+def metric_at_k(name, y, k):
+    y = np.ascontiguousarray(y, np.int32)
+    f = {"DCG": lib().oracle_dcg_at_k, "Recall": lib().oracle_recall_at_k, "MAP": lib().oracle_ap_at_k}[name]
+    return f(_p(y), y.shape[0], k)
