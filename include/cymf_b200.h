@@ -1,0 +1,114 @@
+/* cymf_b200.h -- C ABI of the B200-native factor-update hot path of CyMF.
+ *
+ * This is the drop-in boundary.  The reference (minatosato/cymf) has no FFI layer of its own: its hot
+ * loops are the bodies of four typed Cython methods.  Each group of entry points below replaces one of
+ * them and cites it (paths relative to the reference tree):
+ *
+ *   cymf_rng_*          <- cymf/math.pyx:12-18      UniformGenerator (std::mt19937 + uniform_int_distribution)
+ *   cymf_bpr_*          <- cymf/bpr.pyx:117-171     BPR._fit_bpr      (+ cymf/model.pyx:47-87, cymf/optimizer.pyx)
+ *   cymf_glove_*        <- cymf/glove.pyx:117-156   GloVe._fit_glove  (+ cymf/model.pyx:166-204, optimizer.pyx:85-123)
+ *   cymf_als_*, cymf_gram_* <- cymf/wmf.pyx:136-174 WMF._als          (+ cymf/linalg.pyx:144-163 solvep)
+ *   cymf_eval_*         <- cymf/evaluator.pyx:57-139 Evaluator.evaluate (+ cymf/metrics.pyx:24-125)
+ *
+ * Conventions
+ *   - Plain C types only.  `*_dev` functions take DEVICE pointers and a `cudaStream_t` passed as void*
+ *     (NULL = default stream); they enqueue work and return without synchronising.  `*_host` functions
+ *     take HOST pointers, own their device memory for the duration of the call, and return after the
+ *     results are back in the caller's buffers -- they are what a cgo / JNI / ctypes binding of the
+ *     reference method would call.
+ *   - Return value: 0 on success, a positive cudaError_t value, or a negative CYMF_E* code.
+ *     cymf_last_error() returns a thread-local message for the last non-zero status.  Nothing aborts.
+ *   - Factor matrices are row-major with a row stride `ld` (elements) that must be a multiple of 4 and
+ *     >= K; pad columns must be zero (they stay zero under every update rule here).  Element type is
+ *     selected by `dtype`: CYMF_F32 or CYMF_F64.  The reference computes in f64.
+ *   - CSR `indptr` is int64 on the device (N up to 1e9 for config C5), `indices` int32, rows sorted.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point returns an error.
+ */
+#ifndef CYMF_B200_H
+#define CYMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CYMF_ABI_VERSION 1
+
+enum { CYMF_F32 = 0, CYMF_F64 = 1 };
+enum { CYMF_SGD = 0, CYMF_ADAGRAD = 1, CYMF_ADAM = 2 };
+enum { CYMF_EINVAL = -1, CYMF_ENOMEM = -2, CYMF_EUNSUPPORTED = -3 };
+
+int cymf_abi_version(void);
+const char *cymf_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches counter) */
+int64_t cymf_launch_count(void);
+
+/* ---- host RNG: the reference's negative / candidate stream (cymf/math.pyx:12-18) ------------------- */
+typedef struct cymf_rng cymf_rng;
+cymf_rng *cymf_rng_create(uint32_t seed);
+void cymf_rng_destroy(cymf_rng *g);
+/* `count` draws of uniform_int_distribution<long>(0, n-1)(mt19937), libstdc++ >= 11 semantics */
+int cymf_rng_fill_below(cymf_rng *g, uint32_t n, int32_t *out, int64_t count);
+
+/* ---- layout helpers (device pointers) ------------------------------------------------------------------
+ * The reference keeps W/H as dense f64 [rows, K] NumPy arrays (cymf/bpr.pyx:99-101).  On the device a
+ * factor matrix is [rows, ld] of `dtype` with ld = K rounded up to 4; these convert between the two
+ * (src/dst of the f64 side are dense DEVICE staging buffers) and fill optimizer state. */
+int cymf_pack_rows_dev(const double *src, void *dst, int dtype, int64_t rows, int32_t K, int32_t ld, void *stream);
+int cymf_unpack_rows_dev(const void *src, double *dst, int dtype, int64_t rows, int32_t K, int32_t ld, void *stream);
+int cymf_fill_dev(void *dst, int dtype, int64_t n, double value, void *stream);
+
+/* ---- BPR (cymf/bpr.pyx:160-171) -------------------------------------------------------------------- */
+/* Optimizer state: AdaGrad uses s1 (accumulators, init 1); Adam uses s1 = M, s2 = V (init 0); SGD none. */
+typedef struct {
+    void *W;            /* [U, ld]  user factors                      */
+    void *H;            /* [I, ld]  item factors                      */
+    void *s1W, *s1H;    /* optimizer state, same shape / dtype, or NULL */
+    void *s2W, *s2H;
+} cymf_factors;
+
+/* One Hogwild epoch over the N shuffled (user, positive) pairs (bpr.pyx:162-169): one lane group per
+ * triplet, negative j ~ U[0, I) from Philox4x32-10 keyed by (seed, epoch, l), skipped (not resampled)
+ * when j is a positive of u (bpr.pyx:166-167), lock-free read-modify-write of the three rows.
+ * `scatter`: 0 = plain vector stores (races lose updates, as in the reference), 1 = additive updates are
+ * applied with red.global.add (SGD only).  `max_inflight` > 0 caps the number of triplets processed
+ * concurrently (bounds Hogwild staleness on small matrices; 0 = fill the machine).
+ * `applied` (device uint64, may be NULL) += accepted triplets. */
+int cymf_bpr_hogwild_epoch_dev(const cymf_factors *f, int dtype, int optimizer, int scatter,
+                               const int32_t *users, const int32_t *positives, int64_t N,
+                               const int64_t *indptr, const int32_t *indices,
+                               int32_t U, int32_t I, int32_t K, int32_t ld,
+                               double learning_rate, double weight_decay,
+                               uint64_t seed, uint32_t epoch, int64_t max_inflight,
+                               unsigned long long *applied, void *stream);
+
+/* The negative the Hogwild kernels draw for triplets l = first .. first+count-1 of `epoch` (host-side
+ * evaluation of the same Philox4x32-10 code), so that a run can be audited against the CPU oracle. */
+int cymf_bpr_negatives_host(uint64_t seed, uint32_t epoch, int64_t first, int64_t count, uint32_t n, int32_t *out);
+
+/* Serialized f64 replay of one epoch with a caller-supplied negative stream (device int32[N], e.g. from
+ * cymf_rng_fill_below): triplets are applied strictly in order l = 0..N-1 with the reference's own
+ * operation order (sequential-k dot product, no FMA contraction), i.e. num_threads = 1 semantics. */
+int cymf_bpr_replay_epoch_dev(const cymf_factors *f, int optimizer,
+                              const int32_t *users, const int32_t *positives, const int32_t *negatives,
+                              int64_t N, const int64_t *indptr, const int32_t *indices,
+                              int32_t U, int32_t I, int32_t K, int32_t ld,
+                              double learning_rate, double weight_decay,
+                              unsigned long long *applied, void *stream);
+
+/* Host-buffer form of BPR._fit_bpr(users, positives, X, num_epochs, learning_rate, weight_decay, ...):
+ * W [U,K], H [I,K] are dense row-major f64 HOST arrays updated in place; X is given as host CSR
+ * (int32 indptr / indices, as scipy hands them over).  mode: 0 = Hogwild f32, 1 = Hogwild f64,
+ * 2 = serialized f64 replay of the reference stream (mt19937 seed `seed`).  `applied_out` (may be NULL)
+ * receives the number of accepted triplets summed over epochs. */
+int cymf_bpr_fit_host(double *W, double *H, int32_t U, int32_t I, int32_t K,
+                      const int32_t *users, const int32_t *positives, int64_t N,
+                      const int32_t *indptr, const int32_t *indices,
+                      int32_t num_epochs, double learning_rate, double weight_decay,
+                      int optimizer, int mode, uint64_t seed, int64_t *applied_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CYMF_B200_H */

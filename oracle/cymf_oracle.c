@@ -97,6 +97,8 @@ static int row_contains(const int32_t *indices, int64_t lo, int64_t hi, int32_t 
  * BPR   (cymf/bpr.pyx:140-171, cymf/model.pyx:47-87, cymf/optimizer.pyx:52-58,66-82,127-160)
  *   optimizer: 0 = sgd, 1 = adagrad (accumulators start at ONE), 2 = adam (no timestep, constant
  *   1/(1-beta) correction).  Optimizer state is rebuilt on every call, as every fit() does.
+ *   negatives_in (num_epochs*N, may be NULL) replaces the mt19937 stream with a caller-supplied one
+ *   (used to check the Hogwild kernel, whose negatives come from Philox, one triplet at a time).
  *   negatives_out / applied_out (each num_epochs*N, may be NULL) record the triplet stream so the
  *   CUDA replay kernel can be driven with exactly the reference's (u, i, j, skip) sequence.
  *   loss_out (num_epochs, may be NULL): accum_loss / N of bpr.pyx:168-171.
@@ -105,7 +107,7 @@ int oracle_bpr_fit(double *W, double *H, int32_t U, int32_t I, int32_t K,
                    const int32_t *users, const int32_t *positives, int64_t N,
                    const int32_t *indptr, const int32_t *indices,
                    int32_t num_epochs, double lr, double wd, int32_t optimizer, uint32_t seed,
-                   int32_t *negatives_out, uint8_t *applied_out, double *loss_out) {
+                   const int32_t *negatives_in, int32_t *negatives_out, uint8_t *applied_out, double *loss_out) {
     const double beta1 = 0.9, beta2 = 0.999, eps = 1e-8;
     double *sW1 = NULL, *sH1 = NULL, *sW2 = NULL, *sH2 = NULL;
     size_t nW = (size_t)U * K, nH = (size_t)I * K;
@@ -128,7 +130,8 @@ int oracle_bpr_fit(double *W, double *H, int32_t U, int32_t I, int32_t K,
         double accum = 0.0;
         for (int64_t l = 0; l < N; ++l) {
             int32_t u = users[l], i = positives[l];
-            int32_t j = (int32_t)oracle_rng_below(&gen, (uint32_t)I);       /* bpr.pyx:165 */
+            int32_t j = negatives_in ? negatives_in[(int64_t)epoch * N + l]
+                                     : (int32_t)oracle_rng_below(&gen, (uint32_t)I);   /* bpr.pyx:165 */
             int hit = row_contains(indices, indptr[u], indptr[u + 1], j);   /* bpr.pyx:166 */
             if (negatives_out) negatives_out[(int64_t)epoch * N + l] = j;
             if (applied_out) applied_out[(int64_t)epoch * N + l] = (uint8_t)!hit;

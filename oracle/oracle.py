@@ -44,7 +44,7 @@ def lib():
         _lib.oracle_bpr_fit.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_uint32,
-                                        C.c_void_p, C.c_void_p, C.c_void_p]
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.oracle_als_half.restype = C.c_int
         _lib.oracle_als_half.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_double]
@@ -114,7 +114,7 @@ def bpr_prologue(X, K):
 
 
 def bpr_fit(W, H, users, positives, X, num_epochs, lr, wd, optimizer="sgd", seed=1234,
-            record=False, loss=False):
+            record=False, loss=False, negatives=None):
     """In-place on W, H (float64 C-contiguous). Returns dict with optional negatives/applied/loss."""
     assert W.dtype == np.float64 and H.dtype == np.float64 and W.flags.c_contiguous and H.flags.c_contiguous
     X = X.tocsr()
@@ -127,9 +127,12 @@ def bpr_fit(W, H, users, positives, X, num_epochs, lr, wd, optimizer="sgd", seed
     neg = np.empty(num_epochs * N, np.int32) if record else None
     app = np.empty(num_epochs * N, np.uint8) if record else None
     ls = np.empty(num_epochs, np.float64) if loss else None
+    if negatives is not None:
+        negatives = np.ascontiguousarray(negatives, np.int32)
+        assert negatives.shape[0] == num_epochs * N
     rc = lib().oracle_bpr_fit(_p(W), _p(H), X.shape[0], X.shape[1], W.shape[1], _p(users), _p(positives), N,
                               _p(indptr), _p(indices), num_epochs, lr, wd, OPTIMIZERS[optimizer], seed,
-                              _p(neg), _p(app), _p(ls))
+                              _p(negatives), _p(neg), _p(app), _p(ls))
     if rc:
         raise MemoryError("oracle_bpr_fit")
     return {"negatives": neg, "applied": app, "loss": ls}

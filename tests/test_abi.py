@@ -1,0 +1,78 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/cymf_b200.h declares, the Python binding table covers all of them, and the host-side pieces
+(mt19937 negative stream, argument validation, loud failure without a GPU) behave."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+from cymf_b200 import _lib
+
+HEADER = os.path.join(ROOT, "include", "cymf_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cymf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_symbols()
+    assert len(names) >= 10
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in include/cymf_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "cymf_b200/_lib.py SIGNATURES out of sync with the header"
+    assert _lib.lib().cymf_abi_version() == 1
+
+
+def test_host_rng_matches_libstdcxx_vectors():
+    g = golden("rng.npz")
+    for n in (1682, 26744, 7, 1000003):
+        assert np.array_equal(_lib.HostRng(1234).below(n, 64), g[f"below_{n}_seed1234"])
+    assert np.array_equal(_lib.HostRng(99).below(3, 200), g["below_3_seed99"])
+    r = _lib.HostRng(1234)            # the stream persists across calls (one generator per fit, bpr.pyx:141)
+    a, b = r.below(1682, 10), r.below(1682, 54)
+    assert np.array_equal(np.concatenate([a, b]), g["below_1682_seed1234"])
+
+
+def test_host_rng_long_stream_matches_oracle(oracle):
+    assert np.array_equal(_lib.HostRng(4242).below(26744, 200_000), oracle.Rng(4242).below(26744, 200_000))
+
+
+def test_argument_errors_are_reported_not_fatal():
+    L = _lib.lib()
+    assert L.cymf_rng_fill_below(None, 5, None, 1) == -1
+    assert b"bad argument" in L.cymf_last_error()
+    f = _lib.Factors()
+    rc = L.cymf_bpr_hogwild_epoch_dev(ctypes.byref(f), 0, 0, 0, None, None, 0, None, None, 1, 1, 1, 4, 0.1, 0.1, 0, 0,
+                                      0, None, None)
+    assert rc == -1 and b"null pointer" in L.cymf_last_error()
+
+
+def test_constructor_contract():
+    import cymf_b200 as cymf
+    with pytest.raises(Exception, match="rmsprop is invalid."):
+        cymf.BPR(optimizer="rmsprop")
+    m = cymf.BPR()
+    assert (m.num_components, m.learning_rate, m.optimizer, m.weight_decay) == (20, 0.001, "adam", 0.01)
+    assert m.W is None and m.H is None
+    with pytest.raises(ValueError):
+        m.fit(None)
+    with pytest.raises(ValueError):
+        m.fit([[1, 0], [0, 1]])
+    with pytest.raises(ValueError):
+        m.fit(np.eye(3), early_stopping=True)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import cymf_b200 as cymf
+    with pytest.raises(_lib.CymfError, match="no CPU fallback"):
+        cymf.BPR(4, optimizer="sgd").fit(np.eye(4), num_epochs=1, verbose=False)
