@@ -140,4 +140,7 @@ def download_factor(dev, K, out_f64):
     dtype = F32 if dev.dtype == torch.float32 else F64
     tmp = torch.empty((rows, K), dtype=torch.float64, device=dev.device)
     check(lib().cymf_unpack_rows_dev(ptr(dev), ptr(tmp), dtype, rows, K, ld, stream_ptr()))
-    out_f64[...] = tmp.cpu().numpy()
+    if out_f64.flags.c_contiguous and out_f64.dtype == "float64":
+        torch.from_numpy(out_f64).copy_(tmp)          # straight D2H into the caller's buffer (DMA if it is pinned)
+    else:
+        out_f64[...] = tmp.cpu().numpy()

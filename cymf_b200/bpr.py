@@ -20,6 +20,7 @@ from scipy import sparse
 from sklearn import utils
 
 from . import _lib
+from .host import init_missing_factors
 
 
 def _tqdm(total, verbose, ncols=120):
@@ -90,11 +91,7 @@ class BPR(object):
         if early_stopping and self.valid_evaluator is None:
             raise ValueError()
 
-        if self.W is None:
-            np.random.seed(4321)
-            self.W = np.random.uniform(low=-0.1, high=0.1, size=(X.shape[0], self.num_components)) / self.num_components
-        if self.H is None:
-            self.H = np.random.uniform(low=-0.1, high=0.1, size=(X.shape[1], self.num_components)) / self.num_components
+        init_missing_factors(self, X.shape[0], X.shape[1])               # bpr.pyx:97-101
 
         users, positives = utils.shuffle(*(X.nonzero()))
         return self._fit_bpr(users.astype(np.int32), positives.astype(np.int32), X, num_epochs,
@@ -110,7 +107,7 @@ class BPR(object):
         W, H = self.W, self.H                                    # updated in place, like the reference's views
         sess = BprSession(W, H, users, positives, X, self.optimizer, mode=self.mode, dtype=self.dtype,
                           scatter=self.scatter, seed=self.seed, max_inflight=self.max_inflight, device=self.device)
-        W_best, H_best = W.copy(), H.copy()
+        W_best, H_best = (W.copy(), H.copy()) if valid_evaluator else (None, None)
         count = 0
         with _tqdm(num_epochs, verbose) as progress:
             for epoch in range(num_epochs):

@@ -21,7 +21,7 @@ template <typename T> struct BprArgs {
     const int32_t *users, *positives, *negatives;
     const int64_t *indptr;
     const int32_t *indices;
-    int64_t N;
+    int64_t N, groups;
     int32_t I, ld;
     T lr, wd;
     uint64_t seed;
@@ -61,19 +61,21 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const BprArgs<T> a) {
     const int gshift = (lane / LPT) * LPT;
     const unsigned gmask = group_mask<LPT>(lane);
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t stride = (((int64_t)gridDim.x * blockDim.x) >> 5) * GPW;
+    const int64_t stride = a.groups;                    // active lane groups in the grid (<= launched groups)
     unsigned long long n_applied = 0;
 
-    int64_t l = warp * GPW + lane / LPT;
+    const int64_t gid = warp * GPW + lane / LPT;
+    const bool active = gid < stride;
+    int64_t l = gid;
     int32_t u_next = 0, i_next = 0;
-    if (l < a.N) { u_next = __ldcs(a.users + l); i_next = __ldcs(a.positives + l); }
+    if (active && l < a.N) { u_next = __ldcs(a.users + l); i_next = __ldcs(a.positives + l); }
 
     // warp-uniform trip count: the first group of the warp runs out last
-    for (int64_t base = warp * GPW; base < a.N; base += stride, l += stride) {
-        const bool valid = l < a.N;
+    for (int64_t base = warp * GPW; base < a.N && warp * GPW < stride; base += stride, l += stride) {
+        const bool valid = active && l < a.N;
         const int32_t u = u_next, i = i_next;
         const int64_t ln = l + stride;
-        if (ln < a.N) { u_next = __ldcs(a.users + ln); i_next = __ldcs(a.positives + ln); }
+        if (active && ln < a.N) { u_next = __ldcs(a.users + ln); i_next = __ldcs(a.positives + ln); }
         const int32_t j = (int32_t)philox_negative(a.seed, a.epoch, (uint64_t)l, (uint32_t)a.I);   // bpr.pyx:165
 
         // speculative gathers of the three rows (j is rarely a positive of u), issued before the membership probe
@@ -248,7 +250,10 @@ static int launch_hogwild(const BprArgs<T> &a, int64_t max_groups, cudaStream_t 
     if (blocks > need) blocks = need;
     if (max_groups > 0 && blocks * GPB > max_groups) blocks = (max_groups + GPB - 1) / GPB;
     if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, 256, 0, st>>>(a);
+    BprArgs<T> b = a;
+    b.groups = blocks * GPB;
+    if (max_groups > 0 && b.groups > max_groups) b.groups = max_groups;
+    kern<<<(unsigned)blocks, 256, 0, st>>>(b);
     CYMF_LAUNCHED();
     return 0;
 }

@@ -125,16 +125,24 @@ def _mean_metrics(oracle, W, H, test, train):
 @pytest.mark.parametrize("opt,lr", [("sgd", 0.05), ("adam", 0.01)])
 def test_hogwild_f32_metric_parity_c1(oracle, opt, lr):
     """Config C1 shape: Recall@5 / DCG@5 / MAP@5 of the concurrent f32 kernel within 1 % of the reference's."""
+    # The reference's own metrics move by ~0.4 % (1 sigma) with the negative-sampling seed alone (measured
+    # with the oracle: seeds 1234,1..5 span 1.0-1.9 %), so both sides are averaged over 6 seeds; the standard
+    # error of the difference of means is then ~0.25 % and the 1 % bound is a 4-sigma test.
     import cymf_b200 as cymf
     train, test = cymf.synth.movielens_like("ml-100k")
-    epochs = 30
-    Xc, W, H, users, positives = oracle.bpr_prologue(train, 20)
-    oracle.bpr_fit(W, H, users, positives, Xc, epochs, lr, 0.01, opt)
-    want = _mean_metrics(oracle, W, H, test, train)
-    m = cymf.BPR(20, lr, opt, 0.01)
-    m.fit(train, num_epochs=epochs, num_threads=8, verbose=False)
-    got = _mean_metrics(oracle, m.W, m.H, test, train)
-    print(opt, "reference", want, "gpu", got, "applied", m.n_applied_, "/", m.n_attempted_)
-    assert want["Recall@5"] > 0.1, "synthetic data too flat to detect regressions"
+    epochs, seeds = 30, (1234, 1, 2, 3, 4, 5)
+    wants, gots = [], []
+    for seed in seeds:
+        Xc, W, H, users, positives = oracle.bpr_prologue(train, 20)
+        oracle.bpr_fit(W, H, users, positives, Xc, epochs, lr, 0.01, opt, seed=seed)
+        wants.append(_mean_metrics(oracle, W, H, test, train))
+        m = cymf.BPR(20, lr, opt, 0.01, seed=seed)
+        m.fit(train, num_epochs=epochs, num_threads=8, verbose=False)
+        gots.append(_mean_metrics(oracle, m.W, m.H, test, train))
+        assert 0.8 * m.n_attempted_ < m.n_applied_ < m.n_attempted_
+    want = {k: float(np.mean([r[k] for r in wants])) for k in wants[0]}
+    got = {k: float(np.mean([r[k] for r in gots])) for k in gots[0]}
+    print(opt, "reference", want, "gpu", got)
+    assert want["Recall@5"] > 0.3, "synthetic data too flat to detect regressions"
     for k in want:
         assert abs(got[k] - want[k]) <= 0.01 * want[k], (k, got[k], want[k])
