@@ -23,6 +23,11 @@ class Factors(C.Structure):
     _fields_ = [(n, _p) for n in ("W", "H", "s1W", "s1H", "s2W", "s2H")]
 
 
+class GloveParams(C.Structure):
+    """struct cymf_glove_params"""
+    _fields_ = [(n, _p) for n in ("W", "H", "bW", "bH", "aW", "aH", "abW", "abH")]
+
+
 # name -> (restype, argtypes); must list EVERY symbol include/cymf_b200.h declares (tests check this)
 SIGNATURES = {
     "cymf_abi_version": (C.c_int, []),
@@ -41,6 +46,14 @@ SIGNATURES = {
                                             _i32, _i32, _i32, _i32, _f64, _f64, _p, _p]),
     "cymf_bpr_fit_host": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _i64, _p, _p, _i32, _f64, _f64,
                                     C.c_int, C.c_int, _u64, _p]),
+    "cymf_glove_hogwild_epoch_dev": (C.c_int, [C.POINTER(GloveParams), C.c_int, C.c_int, _p, _p, _p, _i64, _i32, _i32,
+                                               _f64, _f64, _f64, _i64, _p, _p]),
+    "cymf_glove_replay_epoch_dev": (C.c_int, [C.POINTER(GloveParams), _p, _p, _p, _i64, _i32, _i32, _f64, _f64, _f64,
+                                              _p, _p]),
+    "cymf_glove_fit_host": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _f64, _f64, _f64,
+                                      C.c_int, _p]),
+    "cymf_eval_candidates_host": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _i32, _u32, _p, _p, _i64]),
+    "cymf_eval_rank_dev": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p]),
 }
 
 _lib = None

@@ -171,22 +171,6 @@ extern "C" int cymf_fill_dev(void *dst, int dtype, int64_t n, double value, void
 }
 
 // ---- host-buffer BPR fit ---------------------------------------------------------------------------------------
-namespace {
-struct DeviceArena {          // frees everything it handed out when the call returns, on every path
-    std::vector<void *> blocks;
-    ~DeviceArena() { for (void *p : blocks) cudaFree(p); }
-    template <typename P> int get(P **out, size_t bytes) {
-        void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
-        if (e != cudaSuccess) { *out = nullptr; return cuda_status(e, "cudaMalloc", __FILE__, __LINE__); }
-        blocks.push_back(p);
-        *out = (P *)p;
-        return 0;
-    }
-};
-#define CYMF_TRY(expr) do { int rc_ = (expr); if (rc_) return rc_; } while (0)
-}  // namespace
-
 extern "C" int cymf_bpr_fit_host(double *W, double *H, int32_t U, int32_t I, int32_t K,
                                  const int32_t *users, const int32_t *positives, int64_t N,
                                  const int32_t *indptr, const int32_t *indices,

@@ -33,6 +33,40 @@ int sm_count();
         CYMF_CUDA(cudaGetLastError());                             \
     } while (0)
 
+#define CYMF_TRY(expr)             \
+    do {                           \
+        int rc_ = (expr);          \
+        if (rc_) return rc_;       \
+    } while (0)
+
+// Device allocations of one `*_host` call: everything handed out is freed when the call returns, on every path.
+struct DeviceArena {
+    void *blocks[64];
+    int count = 0;
+    ~DeviceArena() {
+        for (int t = 0; t < count; ++t) cudaFree(blocks[t]);
+    }
+    template <typename P> int get(P **out, size_t bytes) {
+        void *p = nullptr;
+        *out = nullptr;
+        if (count >= 64) { set_error("DeviceArena: too many blocks"); return CYMF_ENOMEM; }
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e != cudaSuccess) return cuda_status(e, "cudaMalloc", __FILE__, __LINE__);
+        blocks[count++] = p;
+        *out = (P *)p;
+        return 0;
+    }
+};
+
+// grid for a flat grid-stride kernel of n items (256 threads per block, at most 8 blocks per SM)
+static inline unsigned flat_grid(int64_t n) {
+    int64_t b = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
 // ---- Philox4x32-10 (counter-based; one call per triplet, no state to carry) ---------------------------------
 __host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
 #ifdef __CUDA_ARCH__

@@ -1,0 +1,149 @@
+// eval.cu -- sampled-candidate ranking evaluator (replaces the per-user Python loop of
+// cymf/evaluator.pyx:91-133 and the metric functions of cymf/metrics.pyx:24-43,71-85,109-125).
+//
+//   cymf_eval_candidates_host : the sequential part.  One mt19937 for the whole call, users in index order,
+//                               num_negatives draws per evaluated user with rejection of test+train positives
+//                               (evaluator.pyx:82,95-111).  Inherently serial (each user's stream position depends
+//                               on every earlier rejection), so it runs on the host, once per (evaluator, seed).
+//   eval_rank_kernel          : one CTA per user.  f64 scores with the k-ascending dot of the reference
+//                               (evaluator.pyx:113), exact ranks by counting (score desc, ties by candidate
+//                               position desc = the reverse of a stable ascending argsort), then the three
+//                               metrics accumulated in rank order exactly as metrics.pyx does.
+//                               Bound by the gather of H rows: sum_u n_u (8K + 4) + 8UK bytes.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cymf {
+
+struct EvalArgs {
+    const double *W, *H;
+    const int32_t *test_indptr;
+    const int64_t *cand_ptr;
+    const int32_t *cand_items;
+    const int32_t *ks;            // [nk]
+    const double *log2_table;     // [kmax]: log2(i + 1), evaluated by the host's libm like metrics.pyx:38
+    double *per_user;             // [U, nk, 3]  DCG, Recall, MAP  (evaluator.pyx:87-89 `buff`)
+    int32_t *order;               // per candidate slot: candidate position by rank, or NULL
+    int32_t U, K, nk, kmax;
+};
+
+__global__ void __launch_bounds__(128) eval_rank_kernel(const EvalArgs a) {
+    extern __shared__ double smem[];
+    double *w = smem;                               // [K]
+    double *score = smem + a.K;                     // [n]
+    __shared__ int ysorted[128];                    // feedback of the first kmax ranks (kmax <= 128)
+    for (int u = blockIdx.x; u < a.U; u += gridDim.x) {
+        const int64_t c0 = a.cand_ptr[u];
+        const int n = (int)(a.cand_ptr[u + 1] - c0);
+        double *out = a.per_user + (size_t)u * a.nk * 3;
+        if (n == 0) {                                                           // evaluator.pyx:92-93
+            for (int t = threadIdx.x; t < a.nk * 3; t += blockDim.x) out[t] = 0.0;
+            continue;
+        }
+        const int npos = a.test_indptr[u + 1] - a.test_indptr[u];
+        for (int k = threadIdx.x; k < a.K; k += blockDim.x) w[k] = a.W[(size_t)u * a.K + k];
+        for (int t = threadIdx.x; t < a.kmax; t += blockDim.x) ysorted[t] = 0;
+        __syncthreads();
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {                     // evaluator.pyx:113, k ascending
+            const double *h = a.H + (size_t)a.cand_items[c0 + t] * a.K;
+            double acc = 0.0;
+            for (int k = 0; k < a.K; ++k) acc = __dadd_rn(acc, __dmul_rn(__ldg(h + k), w[k]));
+            score[t] = acc;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            const double mine = score[t];
+            int rank = 0;
+            for (int s = 0; s < n; ++s) {
+                const double other = score[s];
+                rank += (other > mine) || (other == mine && s > t);
+            }
+            if (rank < a.kmax) ysorted[rank] = t < npos;                        // evaluator.pyx:114
+            if (a.order) a.order[c0 + rank] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x < a.nk) {                                               // metrics.pyx, in rank order
+            const int k = a.ks[threadIdx.x];
+            const double total = (double)npos;                                  // `counter` after the full pass
+            double dcg = (double)ysorted[0], rec = 0.0, ap = 0.0, hits = 0.0;
+            for (int i = 0; i < n && i < k; ++i) {
+                const double y = (double)ysorted[i];
+                if (i >= 1) dcg = __dadd_rn(dcg, __ddiv_rn(y, a.log2_table[i]));           // metrics.pyx:37-39
+                rec = __dadd_rn(rec, y);                                                     // metrics.pyx:77-78
+                hits = __dadd_rn(hits, y);
+                if (ysorted[i] == 1) ap = __dadd_rn(ap, __ddiv_rn(hits, (double)i + 1.0));   // metrics.pyx:117-119
+            }
+            out[threadIdx.x * 3 + 0] = npos ? __ddiv_rn(dcg, total) : 0.0;
+            out[threadIdx.x * 3 + 1] = npos ? __ddiv_rn(rec, total) : 0.0;
+            out[threadIdx.x * 3 + 2] = npos ? __ddiv_rn(ap, total) : 0.0;
+        }
+        __syncthreads();
+    }
+}
+
+static bool sorted_row_has(const int32_t *idx, int64_t lo, int64_t end, int32_t key) {
+    int64_t hi = end;
+    while (lo < hi) {                                   // lower bound
+        const int64_t mid = (lo + hi) >> 1;
+        if (idx[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo < end && idx[lo] == key;
+}
+
+}  // namespace cymf
+
+using namespace cymf;
+
+extern "C" int cymf_eval_candidates_host(int32_t U, int32_t I, const int32_t *test_indptr, const int32_t *test_indices,
+                                         const int32_t *all_indptr, const int32_t *all_indices,
+                                         int32_t num_negatives, uint32_t seed, int64_t *cand_ptr, int32_t *cand_items,
+                                         int64_t capacity) {
+    CYMF_REQUIRE(test_indptr && test_indices && all_indptr && all_indices && cand_ptr && cand_items, "null pointer");
+    CYMF_REQUIRE(U > 0 && I > 0 && num_negatives >= 0, "bad shape");
+    cymf_rng *gen = cymf_rng_create(seed);                                      // evaluator.pyx:82
+    if (!gen) { set_error("out of memory"); return CYMF_ENOMEM; }
+    int64_t w = 0;
+    int32_t block[256];
+    int filled = 0, used = 0;
+    cand_ptr[0] = 0;
+    int rc = 0;
+    for (int32_t u = 0; u < U && !rc; ++u) {
+        const int32_t t0 = test_indptr[u], t1 = test_indptr[u + 1];
+        if (t0 != t1) {                                                         // evaluator.pyx:92-93
+            if (w + (t1 - t0) + num_negatives > capacity) { set_error("cand_items too small"); rc = CYMF_EINVAL; break; }
+            for (int32_t p = t0; p < t1; ++p) cand_items[w++] = test_indices[p];
+            const int64_t a0 = all_indptr[u], a1 = all_indptr[u + 1];
+            for (int32_t t = 0; t < num_negatives; ++t) {                       // evaluator.pyx:106-111
+                int32_t item;
+                do {
+                    if (used == filled) { cymf_rng_fill_below(gen, (uint32_t)I, block, 256); filled = 256; used = 0; }
+                    item = block[used++];
+                } while (a1 > a0 && all_indices[a0] <= item && item <= all_indices[a1 - 1] &&
+                         sorted_row_has(all_indices, a0, a1, item));
+                cand_items[w++] = item;
+            }
+        }
+        cand_ptr[u + 1] = w;
+    }
+    cymf_rng_destroy(gen);
+    return rc;
+}
+
+extern "C" int cymf_eval_rank_dev(const double *W, const double *H, int32_t U, int32_t K,
+                                  const int32_t *test_indptr, const int64_t *cand_ptr, const int32_t *cand_items,
+                                  int32_t max_candidates, const int32_t *ks, int32_t nk, const double *log2_table,
+                                  int32_t kmax, double *per_user, int32_t *order, void *stream) {
+    CYMF_REQUIRE(W && H && test_indptr && cand_ptr && cand_items && ks && log2_table && per_user, "null pointer");
+    CYMF_REQUIRE(U > 0 && K > 0 && nk > 0 && nk <= 32 && kmax > 0 && kmax <= 128, "bad shape (1..32 cut-offs, k <= 128)");
+    EvalArgs a{W, H, test_indptr, cand_ptr, cand_items, ks, log2_table, per_user, order, U, K, nk, kmax};
+    const size_t smem = sizeof(double) * ((size_t)K + (size_t)(max_candidates > 0 ? max_candidates : 1));
+    if (smem > 200 * 1024) { set_error("evaluator: %d candidates for one user exceed shared memory", max_candidates); return CYMF_EUNSUPPORTED; }
+    if (smem > 48 * 1024)
+        CYMF_CUDA(cudaFuncSetAttribute(eval_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = (int64_t)sm_count() * 8;
+    if (blocks > U) blocks = U;
+    eval_rank_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(a);
+    CYMF_LAUNCHED();
+    return 0;
+}

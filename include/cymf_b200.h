@@ -108,6 +108,59 @@ int cymf_bpr_fit_host(double *W, double *H, int32_t U, int32_t I, int32_t K,
                       int32_t num_epochs, double learning_rate, double weight_decay,
                       int optimizer, int mode, uint64_t seed, int64_t *applied_out);
 
+/* ---- GloVe (cymf/glove.pyx:149-156, cymf/model.pyx:166-204, cymf/optimizer.pyx:85-123) ---------------- */
+typedef struct {
+    void *W, *H;        /* [Vw, ld] central and [Vh, ld] context word vectors                       */
+    void *bW, *bH;      /* [Vw], [Vh] biases                                                        */
+    void *aW, *aH;      /* AdaGrad accumulators of W, H (same shapes; the reference starts them at 1) */
+    void *abW, *abH;    /* AdaGrad accumulators of the biases                                       */
+} cymf_glove_params;
+
+/* One Hogwild pass over the N shuffled (central, context, count) samples (glove.pyx:151-153).  `counts` has
+ * the element type selected by `dtype`.  scatter: 0 = vector stores, 1 = red.global.add of the AdaGrad
+ * increments and steps.  The reference's K-fold bias update (model.pyx:199-204) is kept.
+ * `loss_sum` (device double, may be NULL) += sum_l 0.5 f(n) d^2 (model.pyx:180). */
+int cymf_glove_hogwild_epoch_dev(const cymf_glove_params *p, int dtype, int scatter,
+                                 const int32_t *central, const int32_t *context, const void *counts,
+                                 int64_t N, int32_t K, int32_t ld, double learning_rate, double x_max,
+                                 double alpha, int64_t max_inflight, double *loss_sum, void *stream);
+
+/* Serialized f64 replay, samples applied in order with the reference's operation order.
+ * `loss` (device double[N], may be NULL) receives loss[l] (glove.pyx:152). */
+int cymf_glove_replay_epoch_dev(const cymf_glove_params *p, const int32_t *central, const int32_t *context,
+                                const double *counts, int64_t N, int32_t K, int32_t ld,
+                                double learning_rate, double x_max, double alpha, double *loss, void *stream);
+
+/* Host-buffer form of GloVe._fit_glove(central_words, context_words, counts, central_W, central_bias,
+ * context_W, context_bias, num_epochs, learning_rate, x_max, alpha, ...): dense f64 HOST arrays updated in
+ * place.  mode as in cymf_bpr_fit_host.  loss_out (num_epochs, may be NULL) = mean loss per epoch. */
+int cymf_glove_fit_host(const int32_t *central, const int32_t *context, const double *counts, int64_t N,
+                        double *central_W, double *central_bias, double *context_W, double *context_bias,
+                        int64_t Vw, int64_t Vh, int32_t K, int32_t num_epochs,
+                        double learning_rate, double x_max, double alpha, int mode, double *loss_out);
+
+/* ---- Evaluator (cymf/evaluator.pyx:57-139, cymf/metrics.pyx:24-125; unbiased=False path) ---------------- */
+/* Candidate lists of Evaluator.evaluate (evaluator.pyx:91-111), HOST arrays in and out: per user with test
+ * items, its test positives in CSR order followed by `num_negatives` draws of the reference's sequential
+ * mt19937 stream (seed), rejecting test+train positives (`all_*`: CSR of test+train, sorted rows).
+ * cand_ptr [U+1] receives offsets into cand_items (`capacity` entries available; the exact need is
+ * nnz(test) + #users_with_test_items * num_negatives). */
+int cymf_eval_candidates_host(int32_t U, int32_t I, const int32_t *test_indptr, const int32_t *test_indices,
+                              const int32_t *all_indptr, const int32_t *all_indices,
+                              int32_t num_negatives, uint32_t seed, int64_t *cand_ptr, int32_t *cand_items,
+                              int64_t capacity);
+
+/* Scoring + ranking + metrics on the device (evaluator.pyx:113-133).  W [U,K], H [I,K] dense f64 (the
+ * reference casts to f64, evaluator.pyx:58-59).  ks [nk] (device) are the cut-offs, log2_table[i] =
+ * log2(i+1) for i < kmax = max(ks) (device; computed by the host's libm as metrics.pyx:38 does).
+ * per_user [U, nk, 3] receives DCG@k, Recall@k, MAP@k of every user (0 for users without test items); the
+ * caller averages over ALL U users (evaluator.pyx:135-137).  order (may be NULL): for every candidate slot
+ * of cand_items, the candidate position holding that rank (descending score, ties by descending position). */
+int cymf_eval_rank_dev(const double *W, const double *H, int32_t U, int32_t K,
+                       const int32_t *test_indptr, const int64_t *cand_ptr, const int32_t *cand_items,
+                       int32_t max_candidates, const int32_t *ks, int32_t nk, const double *log2_table,
+                       int32_t kmax, double *per_user, int32_t *order, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
