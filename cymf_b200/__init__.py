@@ -10,6 +10,7 @@ The CUDA library (cymf_b200/libcymf_b200.so, C ABI in include/cymf_b200.h) is lo
 no CPU fallback -- calls raise when it has not been built or no CUDA device is visible.
 """
 from .bpr import BPR
+from .wmf import WMF
 from .glove import GloVe
 from . import evaluator
 from .evaluator import Evaluator, AverageOverAllEvaluator, AoaEvaluator, UnbiasedEvaluator

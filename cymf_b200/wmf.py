@@ -1,0 +1,284 @@
+"""`cymf.WMF` on B200s: same constructor / `fit` / `_als` signatures and attributes as the reference class
+(cymf/wmf.pyx:32-174); the Gram product and the prange row loop of `_als` (wmf.pyx:142-174) run as CUDA kernels
+(cymf_b200/csrc/als.cu) reached through the C ABI of include/cymf_b200.h.
+
+Host logic kept in Python as in the reference: input coercion and seeded init (wmf.pyx:69-92), the epoch loop
+with per-epoch validation / early stopping (wmf.pyx:110-132).  The reference re-transposes X twice per epoch
+(wmf.pyx:112); here both orientations are built once per fit.
+
+The reference factorises a dense K x K matrix per row with LAPACK dgesv; here each row is solved by conjugate
+gradient to a relative residual `cg_tol` (default 1e-6 in float32, 1e-10 in float64), which keeps W and H
+within 1e-4 (relative) of the reference's -- see tests/test_wmf_gpu.py.
+
+Multi-GPU (one process per GPU, torch.distributed/NCCL already initialised): rows of each half sweep are
+partitioned over the ranks (heaviest-first round-robin deal, so row counts are equal and nnz is balanced), every
+rank holds a full replica of both factor matrices, solves its own block, then the blocks are all-gathered and the
+K x K Gram partials of the freshly solved blocks are all-reduced.  world_size == 1 runs the same code.
+"""
+import ctypes as C
+
+import numpy as np
+from scipy import sparse
+
+from . import _lib
+from .host import init_missing_factors
+
+
+class WMF(object):
+    """
+    Weighted Matrix Factorization (WMF), http://yifanhu.net/PUB/cf.pdf
+
+    Attributes:
+        num_components (int): A dimensionality of latent vector
+        weight_decay (double): A coefficient of weight decay
+        weight (double): A weight for positive feedbacks.
+        W (np.ndarray[double, ndim=2]): User latent vectors
+        H (np.ndarray[double, ndim=2]): Item latent vectors
+    """
+
+    def __init__(self, num_components=20, weight_decay=0.01, weight=10.0, *, dtype="float32", cg_tol=None,
+                 cg_max_iter=None, device=None, distributed="auto"):
+        self.num_components = int(num_components)
+        self.weight_decay = float(weight_decay)
+        self.weight = float(weight)
+        self.W = None
+        self.H = None
+        if dtype not in _lib.DTYPES:
+            raise ValueError("dtype must be 'float32' or 'float64'")
+        if self.num_components > 128:
+            raise ValueError("cymf_b200.WMF supports num_components <= 128")
+        self.dtype = dtype
+        self.cg_tol = cg_tol
+        self.cg_max_iter = cg_max_iter
+        self.device = device
+        self.distributed = distributed
+        self.cg_iterations_ = 0          # CG iterations summed over rows, last fit
+        self.cg_unconverged_ = 0         # rows that stopped at cg_max_iter, last fit
+
+    def fit(self, X, num_epochs=5, num_threads=1, valid_evaluator=None, early_stopping=False, verbose=True):
+        """
+        Training WMF model with ALS.
+
+        Args:
+            X: A user-item interaction matrix.
+            num_epochs (int): A number of epochs.
+            num_threads (int): accepted for signature compatibility; the GPU grid replaces the thread pool.
+            verbose (bool): Whether to show the progress of training.
+        """
+        if X is None:
+            raise ValueError()
+        if sparse.isspmatrix(X):
+            X = X.tocsr()
+        elif isinstance(X, np.ndarray):
+            X = sparse.csr_matrix(X)
+        else:
+            raise ValueError()
+        X = X.astype(np.float64)
+
+        self.valid_evaluator = valid_evaluator
+        self.valid_dcg = -np.inf
+        self.count = 0
+        self.early_stopping = early_stopping
+        if early_stopping and self.valid_evaluator is None:
+            raise ValueError()
+        init_missing_factors(self, X.shape[0], X.shape[1])               # wmf.pyx:88-92
+        self._fit_als(X, num_epochs, num_threads, verbose)
+
+    def _tolerances(self):
+        tol = self.cg_tol if self.cg_tol is not None else (1e-6 if self.dtype == "float32" else 1e-10)
+        iters = self.cg_max_iter if self.cg_max_iter is not None else 2 * self.num_components
+        return float(tol), int(iters)
+
+    def _fit_als(self, X, num_epochs, num_threads, verbose):
+        """Device replacement of `WMF._fit_als` (wmf.pyx:97-132)."""
+        from tqdm import tqdm
+        valid_evaluator = getattr(self, "valid_evaluator", None)
+        early_stopping = getattr(self, "early_stopping", False)
+        self.W = np.ascontiguousarray(self.W, dtype=np.float64)
+        self.H = np.ascontiguousarray(self.H, dtype=np.float64)
+        W, H = self.W, self.H
+        tol, iters = self._tolerances()
+        sess = AlsSession(X, W, H, self.weight_decay, self.weight, dtype=self.dtype, cg_tol=tol, cg_max_iter=iters,
+                          device=self.device, distributed=self.distributed)
+        W_best, H_best = (W.copy(), H.copy()) if valid_evaluator else (None, None)
+        count = 0
+        with tqdm(total=num_epochs, leave=True, ncols=100, disable=not verbose) as progress:
+            for epoch in range(num_epochs):
+                sess.epoch()
+                if valid_evaluator:
+                    sess.download(W, H)
+                    valid_dcg = valid_evaluator.evaluate(W, H)["DCG@5"]
+                    if early_stopping and self.valid_dcg > valid_dcg and count > 10:
+                        break
+                    elif early_stopping and self.valid_dcg > valid_dcg:
+                        count += 1
+                    else:
+                        count = 0
+                        self.valid_dcg = valid_dcg
+                        W_best, H_best = W.copy(), H.copy()
+                progress.set_description(
+                    f"EPOCH={epoch+1:{len(str(num_epochs))}} "
+                    f"{(', DCG@5=' + str(np.round(valid_dcg, 3))) if valid_evaluator else ''}")
+                progress.update(1)
+        sess.download(W, H)
+        self.cg_iterations_, self.cg_unconverged_ = sess.stats()
+        if valid_evaluator and early_stopping:
+            self.W = W_best.copy()
+            self.H = H_best.copy()
+
+    def _als(self, indptr, indices, X, Y, num_threads=1):
+        """`WMF._als(indptr, indices, X, Y, num_threads)` (wmf.pyx:136): solves every row of the HOST array X in
+        place from the HOST array Y; goes through the host-buffer C entry point."""
+        _lib.require_cuda()
+        if not (isinstance(X, np.ndarray) and X.dtype == np.float64 and X.flags.c_contiguous):
+            raise ValueError("X must be a C-contiguous float64 array")
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        ip = np.ascontiguousarray(indptr, np.int32)
+        ix = np.ascontiguousarray(indices, np.int32)
+        tol, iters = self._tolerances()
+        done = C.c_int64(0)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        _lib.check(_lib.lib().cymf_als_half_host(p(ip), p(ix), p(X), p(Y), X.shape[0], Y.shape[0], X.shape[1],
+                                                 self.weight_decay, self.weight, _lib.DTYPES[self.dtype], tol, iters,
+                                                 C.byref(done)))
+        self.cg_iterations_ = int(done.value)
+
+
+def _deal(degrees, world):
+    """Heaviest-first round-robin deal of rows to ranks.  Returns (slot -> old row id or -1, rows per rank):
+    rank r owns the contiguous slots [r*R, (r+1)*R), sorted by decreasing degree, phantoms (-1) at the end."""
+    n = degrees.shape[0]
+    by_weight = np.argsort(-degrees, kind="stable")
+    R = (n + world - 1) // world
+    slots = np.full(R * world, -1, dtype=np.int64)
+    for r in range(world):
+        mine = by_weight[r::world]
+        slots[r * R:r * R + mine.shape[0]] = mine
+    return slots, R
+
+
+def _relabel(Xcsr, row_slots, col_new_index, n_cols):
+    """CSR whose row q is old row row_slots[q] (empty for phantoms) with columns renamed by col_new_index."""
+    ext = sparse.vstack([Xcsr, sparse.csr_matrix((1, Xcsr.shape[1]))]).tocsr()
+    rows = np.where(row_slots >= 0, row_slots, Xcsr.shape[0])
+    P = ext[rows]
+    return sparse.csr_matrix((P.data, col_new_index[P.indices].astype(np.int32), P.indptr),
+                             shape=(rows.shape[0], n_cols))
+
+
+class AlsSession(object):
+    """Device-resident state of one `_fit_als` call (both CSR orientations of this rank's row blocks, full
+    replicas of W and H in dealt order); `epoch()` = user half sweep + item half sweep (wmf.pyx:111-112)."""
+
+    def __init__(self, X, W, H, weight_decay, weight, *, dtype="float32", cg_tol=1e-6, cg_max_iter=128, device=None,
+                 distributed="auto", stage_rows=0):
+        torch = _lib.require_cuda()
+        import torch.distributed as dist
+        self._L = _lib.lib()
+        self.dist = dist if (distributed in ("auto", True) and dist.is_available() and dist.is_initialized()
+                             and dist.get_world_size() > 1) else None
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.rank = self.dist.get_rank() if self.dist else 0
+        self.dev = dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.dtype = _lib.DTYPES[dtype]
+        self.tdt = tdt = torch.float32 if self.dtype == _lib.F32 else torch.float64
+        self.K = K = W.shape[1]
+        self.ld = ld = _lib.ld_for(K)
+        self.wd, self.weight = float(weight_decay), float(weight)
+        self.cg_tol, self.cg_max_iter, self.stage_rows = float(cg_tol), int(cg_max_iter), int(stage_rows)
+        X = X.tocsr()
+        self.U, self.I = U, I = X.shape
+        XT = X.T.tocsr()
+        # dealt (permuted + padded) index spaces of users and items
+        self.slot_u, self.Ru = _deal(np.diff(X.indptr), self.world)
+        self.slot_i, self.Ri = _deal(np.diff(XT.indptr), self.world)
+        new_u = np.empty(U, np.int64); new_u[self.slot_u[self.slot_u >= 0]] = np.flatnonzero(self.slot_u >= 0)
+        new_i = np.empty(I, np.int64); new_i[self.slot_i[self.slot_i >= 0]] = np.flatnonzero(self.slot_i >= 0)
+        Up, Ip = self.slot_u.shape[0], self.slot_i.shape[0]
+        lo_u, lo_i = self.rank * self.Ru, self.rank * self.Ri
+        blk_u = _relabel(X, self.slot_u[lo_u:lo_u + self.Ru], new_i, Ip)
+        blk_i = _relabel(XT, self.slot_i[lo_i:lo_i + self.Ri], new_u, Up)
+        self.nnz = int(X.nnz)
+        self.block_nnz = (int(blk_u.nnz), int(blk_i.nnz))
+        with torch.cuda.device(dev):
+            def up(a, dt):
+                return torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev, non_blocking=True)
+            self.csr_u = (up(blk_u.indptr, np.int64), up(blk_u.indices, np.int32))
+            self.csr_i = (up(blk_i.indptr, np.int64), up(blk_i.indices, np.int32))
+            self.order_u = torch.arange(self.Ru, dtype=torch.int32, device=dev)
+            self.order_i = torch.arange(self.Ri, dtype=torch.int32, device=dev)
+            self.dW = self._upload(W, self.slot_u)
+            self.dH = self._upload(H, self.slot_i)
+            nws = int(self._L.cymf_gram_workspace_doubles(max(Up, Ip), K))
+            self.ws = torch.empty(max(nws, 1), dtype=torch.float64, device=dev)
+            self.g64 = torch.empty(K * K, dtype=torch.float64, device=dev)
+            self.G = torch.empty(K * K, dtype=tdt, device=dev)
+            self.queue = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.d_stats = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.epochs_done = 0
+        self.h2d_bytes = W.nbytes + H.nbytes + 8 * (self.Ru + self.Ri + 2) + 4 * (blk_u.nnz + blk_i.nnz)
+        self.d2h_bytes = W.nbytes + H.nbytes
+
+    def _upload(self, host, slots):
+        """Dense f64 [rows, K] -> device [len(slots), ld] in dealt order (phantom rows zero)."""
+        import torch
+        dealt = np.zeros((slots.shape[0], host.shape[1]), np.float64)
+        dealt[slots >= 0] = host[slots[slots >= 0]]
+        return _lib.upload_factor(dealt, self.dtype, self.dev)
+
+    # one half sweep: solve `rows_side` from the fixed side (wmf.pyx:136-174)
+    def _half(self, X_full, R, csr, order, Y_full, Ry):
+        import torch
+        L, K, ld = self._L, self.K, self.ld
+        stream = _lib.stream_ptr()
+        es = 4 if self.dtype == _lib.F32 else 8
+        if self.dist:
+            # Gram partial over this rank's block of Y, all-reduced over NVLink, then + wd I  (wmf.pyx:142-143)
+            y_blk = Y_full[self.rank * Ry:(self.rank + 1) * Ry]
+            _lib.check(L.cymf_gram_dev(_lib.ptr(y_blk), self.dtype, Ry, K, ld, self.wd, 0, _lib.ptr(self.ws),
+                                       self.ws.numel(), _lib.ptr(self.g64), None, stream))
+            self.dist.all_reduce(self.g64)
+            _lib.check(L.cymf_gram_finalize_dev(_lib.ptr(self.g64), self.dtype, K, self.wd, _lib.ptr(self.G), stream))
+        else:
+            _lib.check(L.cymf_gram_dev(_lib.ptr(Y_full), self.dtype, Y_full.shape[0], K, ld, self.wd, 1,
+                                       _lib.ptr(self.ws), self.ws.numel(), _lib.ptr(self.g64), _lib.ptr(self.G), stream))
+        x_blk = X_full[self.rank * R:(self.rank + 1) * R]
+        _lib.check(L.cymf_als_cg_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order), R, _lib.ptr(x_blk),
+                                     _lib.ptr(Y_full), _lib.ptr(self.G), self.dtype, K, ld, ld, self.weight, self.cg_tol,
+                                     self.cg_max_iter, self.stage_rows, _lib.ptr(self.queue), _lib.ptr(self.d_stats),
+                                     stream))
+        if self.dist:
+            self.dist.all_gather_into_tensor(X_full, x_blk)
+
+    def user_half(self):
+        self._half(self.dW, self.Ru, self.csr_u, self.order_u, self.dH, self.Ri)
+
+    def item_half(self):
+        self._half(self.dH, self.Ri, self.csr_i, self.order_i, self.dW, self.Ru)
+
+    def epoch(self):
+        import torch
+        with torch.cuda.device(self.dev):
+            self.user_half()
+            self.item_half()
+        self.epochs_done += 1
+
+    def download(self, W, H):
+        import torch
+        with torch.cuda.device(self.dev):
+            for dev_m, slots, out in ((self.dW, self.slot_u, W), (self.dH, self.slot_i, H)):
+                dealt = np.empty((slots.shape[0], self.K), np.float64)
+                _lib.download_factor(dev_m, self.K, dealt)
+                out[slots[slots >= 0]] = dealt[slots >= 0]
+
+    def stats(self):
+        s = self.d_stats.cpu().numpy()
+        return int(s[0]), int(s[1])
+
+    @property
+    def bytes_per_epoch(self):
+        """Algorithmic bytes of one epoch (both half sweeps), SURVEY.md 8(d):
+        per half N (K s + 4) + rows (K s + 8) + n K s."""
+        s = 4 if self.dtype == _lib.F32 else 8
+        K, N, U, I = self.K, self.nnz, self.U, self.I
+        return 2 * N * (K * s + 4) + (U + I) * (K * s + 8) + (U + I) * K * s

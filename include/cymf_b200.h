@@ -139,6 +139,38 @@ int cymf_glove_fit_host(const int32_t *central, const int32_t *context, const do
                         int64_t Vw, int64_t Vh, int32_t K, int32_t num_epochs,
                         double learning_rate, double x_max, double alpha, int mode, double *loss_out);
 
+/* ---- WMF ALS (cymf/wmf.pyx:136-174, cymf/linalg.pyx:144-163) ------------------------------------------- */
+/* G = Y^T Y (+ weight_decay * I when add_weight_decay != 0), wmf.pyx:142-143.  Y is [n, ld] of `dtype`.
+ * `workspace` needs cymf_gram_workspace_doubles(n, K) doubles (per-slab partials, reduced in a fixed order so
+ * the result is deterministic).  out_f64 (K*K doubles) and/or out_native (K*K of `dtype`) receive the result.
+ * Multi-GPU: each rank calls this on its own row block with add_weight_decay = 0, all-reduces out_f64 and
+ * finishes with cymf_gram_finalize_dev. */
+int64_t cymf_gram_workspace_doubles(int64_t n, int32_t K);
+int cymf_gram_dev(const void *Y, int dtype, int64_t n, int32_t K, int32_t ld, double weight_decay,
+                  int add_weight_decay, double *workspace, int64_t workspace_doubles,
+                  double *out_f64, void *out_native, void *stream);
+int cymf_gram_finalize_dev(const double *in_f64, int dtype, int32_t K, double weight_decay, void *out_native,
+                           void *stream);
+
+/* Solves the rows listed in `order` (n_solve row ids, heaviest first) of
+ *     (G + (weight-1) sum_{i in row} y_i y_i^T) x = weight sum_{i in row} y_i            (wmf.pyx:158-168)
+ * by conjugate gradient, warm-started from the current content of X, until |residual| <= cg_tol * |rhs| or
+ * cg_max_iter iterations; rows without entries are zeroed (wmf.pyx:154-156).  The K x K matrix the reference
+ * builds and LU-factorises is never formed.  stage_rows: item vectors per row kept in shared memory
+ * (0 = auto).  queue: device int32 scratch (work-queue head).  stats (device uint64[2], may be NULL):
+ * [0] += CG iterations over all rows, [1] += rows that stopped at cg_max_iter (the reference drops dgesv's
+ * `info`; this is the equivalent health signal). */
+int cymf_als_cg_dev(const int64_t *indptr, const int32_t *indices, const int32_t *order, int32_t n_solve,
+                    void *X, const void *Y, const void *G, int dtype, int32_t K, int32_t ldx, int32_t ldy,
+                    double weight, double cg_tol, int32_t cg_max_iter, int32_t stage_rows,
+                    int32_t *queue, unsigned long long *stats, void *stream);
+
+/* Host-buffer form of WMF._als(indptr, indices, X, Y, num_threads): X [rows,K], Y [n,K] dense f64 HOST arrays,
+ * host CSR (int32), X solved in place.  dtype selects the device arithmetic (CYMF_F32 / CYMF_F64). */
+int cymf_als_half_host(const int32_t *indptr, const int32_t *indices, double *X, const double *Y,
+                       int64_t rows, int64_t n, int32_t K, double weight_decay, double weight,
+                       int dtype, double cg_tol, int32_t cg_max_iter, int64_t *cg_iterations_out);
+
 /* ---- Evaluator (cymf/evaluator.pyx:57-139, cymf/metrics.pyx:24-125; unbiased=False path) ---------------- */
 /* Candidate lists of Evaluator.evaluate (evaluator.pyx:91-111), HOST arrays in and out: per user with test
  * items, its test positives in CSR order followed by `num_negatives` draws of the reference's sequential

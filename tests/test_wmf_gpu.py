@@ -1,0 +1,105 @@
+"""GPU parity tests of the WMF ALS path (pytest -m gpu), through the C ABI.
+
+Bar (BASELINE.json): factors within 1e-4 relative of the reference on the same init.  "Relative" is
+max|got - want| / max|want| per matrix.  The reference solves each row exactly (LU); the kernels run conjugate
+gradient to a relative residual of 1e-6 (f32) / 1e-10 (f64):
+  * float64 arithmetic: <= 1e-7 against the compiled reference's recorded factors (tests/golden) after every epoch;
+  * float32 arithmetic (the throughput mode): <= 1e-4 after 1, 2 and 3 epochs on the goldens, and after 2 epochs on
+    the ml-1m-shaped config C2 (K=64) against the oracle.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+from scipy import sparse
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(got, want):
+    return float(np.abs(got - want).max() / np.abs(want).max())
+
+
+def _csr(g):
+    U, I, K = (int(v) for v in g["shape"])
+    return sparse.csr_matrix((np.ones(g["indices"].shape[0]), g["indices"], g["indptr"]), shape=(U, I)), U, I, K
+
+
+@pytest.mark.parametrize("name", ["wmf_small", "wmf_k64"])
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-7), ("float32", 1e-4)])
+def test_fit_matches_reference_golden(name, dtype, tol):
+    import cymf_b200 as cymf
+    g = golden(name + ".npz")
+    X, U, I, K = _csr(g)
+    m = cymf.WMF(K, float(g["wd"]), float(g["weight"]), dtype=dtype)
+    m.W, m.H = g["W0"].copy(), g["H0"].copy()
+    m.fit(X, 1, 4, verbose=False)
+    print(name, dtype, "epoch 1 rel err", _rel(m.W, g["W_e1"]), _rel(m.H, g["H_e1"]), "cg iters", m.cg_iterations_)
+    assert _rel(m.W, g["W_e1"]) <= tol and _rel(m.H, g["H_e1"]) <= tol
+    m.fit(X, int(g["epochs"]) - 1, 4, verbose=False)          # warm start continues from W, H (wmf.pyx:88-92)
+    print(name, dtype, "final rel err", _rel(m.W, g["W"]), _rel(m.H, g["H"]))
+    assert _rel(m.W, g["W"]) <= tol and _rel(m.H, g["H"]) <= tol
+    assert not m.W[3].any() and not m.H[5].any()              # rows without interactions are zeroed (wmf.pyx:154-156)
+    assert m.cg_unconverged_ == 0
+
+
+def test_als_typed_boundary_host_buffers(oracle):
+    """WMF._als(indptr, indices, X, Y, num_threads) with host arrays, one half sweep, vs the oracle."""
+    import cymf_b200 as cymf
+    g = golden("wmf_k64.npz")
+    X, U, I, K = _csr(g)
+    for dtype, tol in (("float64", 1e-8), ("float32", 2e-5)):
+        W, H = g["W0"].copy(), g["H0"].copy()
+        Wo = W.copy()
+        oracle.als_half(X.indptr, X.indices, Wo, H, float(g["wd"]), float(g["weight"]))
+        m = cymf.WMF(K, float(g["wd"]), float(g["weight"]), dtype=dtype)
+        m._als(X.indptr, X.indices, W, H, 8)
+        assert _rel(W, Wo) <= tol
+        assert m.cg_iterations_ > 0
+
+
+def test_gram_kernel(oracle):
+    import torch
+    from cymf_b200 import _lib
+    rng = np.random.default_rng(0)
+    for n, K in ((1000, 20), (5000, 64), (777, 128), (3, 8)):
+        Y = rng.normal(size=(n, K))
+        want = Y.T @ Y + 0.01 * np.eye(K)
+        for dtype, tol in ((_lib.F64, 1e-13), (_lib.F32, 2e-6)):
+            dY = _lib.upload_factor(Y, dtype, torch.device("cuda"))
+            nws = int(_lib.lib().cymf_gram_workspace_doubles(n, K))
+            ws = torch.empty(nws, dtype=torch.float64, device="cuda")
+            g64 = torch.empty(K * K, dtype=torch.float64, device="cuda")
+            _lib.check(_lib.lib().cymf_gram_dev(_lib.ptr(dY), dtype, n, K, dY.shape[1], 0.01, 1, _lib.ptr(ws), nws,
+                                                _lib.ptr(g64), None, None))
+            got = g64.cpu().numpy().reshape(K, K)
+            assert _rel(got, want) <= tol
+            assert np.array_equal(got, got.T)                  # bitwise symmetric (fixed summation order)
+
+
+def test_c2_shape_f32_within_1e4(oracle):
+    """Config C2: K=64 on the ml-1m-shaped matrix, 2 epochs, float32 CG vs the oracle's exact solves."""
+    import cymf_b200 as cymf
+    train, _ = cymf.synth.movielens_like("ml-1m")
+    Wo, Ho = oracle.wmf_fit(train, 64, 0.01, 10.0, 2)
+    m = cymf.WMF(64, 0.01, 10.0)
+    m.fit(train, 2, 8, verbose=False)
+    rows = train.shape[0] + train.shape[1]
+    print("C2 rel err", _rel(m.W, Wo), _rel(m.H, Ho), "mean CG iterations/row", m.cg_iterations_ / (2 * rows))
+    assert _rel(m.W, Wo) <= 1e-4 and _rel(m.H, Ho) <= 1e-4
+    assert m.cg_unconverged_ == 0
+
+
+def test_evaluator_hook_and_early_stopping():
+    import cymf_b200 as cymf
+    train, test = cymf.synth.movielens_like("ml-100k")
+    ev = cymf.evaluator.AverageOverAllEvaluator(test, train, k=5)
+    m = cymf.WMF(20, 0.01, 10.0)
+    m.fit(train, 4, 8, valid_evaluator=ev, early_stopping=True, verbose=False)
+    assert m.valid_dcg > 0.2 and m.W.shape == (943, 20) and m.H.shape == (1682, 20)
+    with pytest.raises(ValueError):
+        cymf.WMF().fit(train, early_stopping=True)
+    with pytest.raises(ValueError):
+        cymf.WMF().fit(None)
