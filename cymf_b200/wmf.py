@@ -179,7 +179,7 @@ class AlsSession(object):
                              and dist.get_world_size() > 1) else None
         self.world = self.dist.get_world_size() if self.dist else 1
         self.rank = self.dist.get_rank() if self.dist else 0
-        self.dev = dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.dev = dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.dtype = _lib.DTYPES[dtype]
         self.tdt = tdt = torch.float32 if self.dtype == _lib.F32 else torch.float64
         self.K = K = W.shape[1]
