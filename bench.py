@@ -157,6 +157,84 @@ def time_bpr_e2e(train, users, positives, K, optimizer, steps, warmup, lr=LR, wd
     return dt, applied, h2d, d2h
 
 
+def time_als(train, K, dtype, steps, warmup, sync_all, world, hbm):
+    """WMF ALS epochs (user + item half sweep), factors and CSR blocks resident; sharded when world > 1."""
+    import torch
+    import torch.distributed as dist
+    from cymf_b200.wmf import AlsSession
+    from cymf_b200.host import init_factors
+    W, H = init_factors(train.shape[0], train.shape[1], K)
+    s = AlsSession(train, W, H, 0.01, 10.0, dtype=dtype, cg_tol=1e-6 if dtype == "float32" else 1e-10,
+                   cg_max_iter=2 * K)
+    for _ in range(warmup):
+        s.epoch()
+    sync_all()
+    it0 = s.stats()[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        s.epoch()
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3 / steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t[0])
+    rows = (train.shape[0] + train.shape[1]) / world
+    out = {"sec_per_epoch": sec, "n_gpus": world, "nnz": int(train.nnz), "K": K, "dtype": dtype,
+           "cg_iterations_per_row": (s.stats()[0] - it0) / (steps * 2 * rows) * 2, "cg_tol": s.cg_tol,
+           "unconverged_rows": s.stats()[1], "algorithmic_GBps": s.bytes_per_epoch / sec / 1e9,
+           "frac_of_hbm_peak": s.bytes_per_epoch / sec / 1e9 / (hbm * world)}
+    del s
+    torch.cuda.empty_cache()
+    return out
+
+
+def synth_cooc_device(V, nnz, seed):
+    """Device-side twin of cymf_b200.synth.synth_cooc (Zipf rows/cols, log-normal counts) for the 1e8-sample config."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    cdf = torch.cumsum(1.0 / (torch.arange(V, device="cuda", dtype=torch.float64) + 1.0), 0)
+    cdf /= cdf[-1].clone()
+    keys = torch.empty(0, dtype=torch.int64, device="cuda")
+    while keys.numel() < nnz:
+        m = int((nnz - keys.numel()) * 1.3) + 1024
+        r = torch.searchsorted(cdf, torch.rand(m, generator=g, device="cuda", dtype=torch.float64)).clamp_(max=V - 1)
+        c = torch.searchsorted(cdf, torch.rand(m, generator=g, device="cuda", dtype=torch.float64)).clamp_(max=V - 1)
+        keys = torch.unique(torch.cat([keys, r * V + c]))
+    keys = keys[torch.randperm(keys.numel(), generator=g, device="cuda")[:nnz]]       # shuffled, as fit() does
+    counts = torch.exp(torch.randn(nnz, generator=g, device="cuda", dtype=torch.float64) * 1.5).clamp_(min=0.1)
+    return (keys // V).to(torch.int32), (keys % V).to(torch.int32), counts
+
+
+def time_glove(V, nnz, K, steps, warmup, hbm):
+    """GloVe AdaGrad epochs on a synthetic V-word vocabulary (BASELINE.json configs[3] shape), f32, device-resident."""
+    import torch
+    from cymf_b200.glove import GloveSession
+    c, x, n = synth_cooc_device(V, nnz, 103)
+    rng = np.random.default_rng(103)
+    W, H = rng.uniform(-.5, .5, (V, K)) / K, rng.uniform(-.5, .5, (V, K)) / K
+    bw, bh = rng.uniform(-.5, .5, V) / K, rng.uniform(-.5, .5, V) / K
+    s = GloveSession(c.cpu().numpy(), x.cpu().numpy(), n.cpu().numpy(), W, bw, H, bh, dtype="float32")
+    del c, x, n
+    for _ in range(warmup):
+        s.epoch(0.05, 10.0, 0.75)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        last = s.epoch(0.05, 10.0, 0.75, want_loss=False)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / steps
+    out = {"samples_per_s": nnz / sec, "sec_per_epoch": sec, "V": V, "nnz": nnz, "K": K,
+           "algorithmic_GBps": nnz * s.bytes_per_sample / sec / 1e9,
+           "frac_of_hbm_peak": nnz * s.bytes_per_sample / sec / 1e9 / hbm}
+    del s
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_reference_bpr(train, users, positives, K, optimizer, budget_s=20.0, threads=None, epochs=None):
     """The compiled reference (oracle/_ref) on a row-block sample; setup removed by differencing two fits."""
     sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
@@ -209,6 +287,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--full", action="store_true", help="GloVe extra at the full 1e8 co-occurrences of configs[3]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
     if args.impl == "reference":
@@ -281,6 +360,18 @@ def main():
                           "frac_of_hbm_peak": a_ * ss.bytes_per_update / s_ / 1e9 / hbm}
             del ss
             torch.cuda.empty_cache()
+    if not args.no_extra:
+        # WMF ALS shards over the ranks (row blocks, all-gather + Gram all-reduce): every rank takes part
+        for tag, name, K in (("wmf_als_f32_k64_ml1m", "ml-1m", 64), ("wmf_als_f32_k128_ml20m", "ml-20m", 128)):
+            if rank == 0:
+                dataset(name)
+            sync_all()
+            res = time_als(dataset(name)[0], K, "float32", max(3, args.steps // 2), 3, sync_all, world, hbm)
+            if rank == 0:
+                extra[tag] = res
+        if rank == 0:
+            extra["glove_adagrad_f32_k300"] = time_glove(400_000, 100_000_000 if args.full else 20_000_000, 300,
+                                                         max(3, args.steps // 2), 3, hbm)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
