@@ -6,13 +6,19 @@
 // Here the matrix is never formed:
 //   gram_partial_kernel / gram_finish_kernel : G (wmf.pyx:142-143).  Row slabs -> per-slab K x K partials (f32 or
 //       f64 products, f64 cross-slab sum) -> deterministic reduction; in multi-GPU runs the partial of a rank's own
-//       row block is all-reduced before wd*I is added.
+//       row block is all-reduced before wd*I is added.  G is handed to the solver as [ld, ld] with zero padding.
 //   als_cg_kernel : one 128-thread CTA per row, conjugate gradient on A p = G p + (w-1) sum_i y_i (y_i . p).
 //       The row's item vectors are staged once in shared memory (as many as fit the staging budget; the rest is
-//       re-read through L2 each iteration), warps split the items, the residual recurrence runs until
-//       |r| <= tol |b| (warm start from the current x_r).  Rows come from a heaviest-first work queue.
+//       re-read through L2 each iteration).  Every lane owns a 1/2/4-element slice of the K-vectors (128-bit
+//       shared/global accesses at K=128); the four warps split the items AND the rows of G, so one per-warp partial
+//       vector carries both terms; dots of four items are reduced with one 10-shuffle butterfly.  The residual
+//       recurrence runs until |r| <= tol |b| (warm start from the current x_r).  Rows come from a heaviest-first
+//       work queue.
 //   Algorithmic bytes per half sweep: N (K s + 4) + rows (K s + 8) + n K s.
 #include <math.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -84,16 +90,20 @@ __global__ void __launch_bounds__(256) gram_partial_kernel(const T *__restrict__
         }
 }
 
-// sum the slab partials in slab order (deterministic), optionally add wd on the diagonal, write f64 and/or T
+// Sum the slab partials in slab order (deterministic), optionally add wd on the diagonal.  out64: dense [K, K] f64;
+// outT: [ld, ld] of T with zero padding (the layout the CG kernel reads).
 template <typename T>
-__global__ void gram_finish_kernel(const double *__restrict__ partial, int slabs, int K, double wd,
+__global__ void gram_finish_kernel(const double *__restrict__ partial, int slabs, int K, int ld, double wd,
                                    double *__restrict__ out64, T *__restrict__ outT) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= K * K) return;
+    if (t >= ld * ld) return;
+    const int i = t / ld, j = t - i * ld;
     double s = 0.0;
-    for (int b = 0; b < slabs; ++b) s += partial[(size_t)b * K * K + t];
-    if (t / K == t % K) s += wd;
-    if (out64) out64[t] = s;
+    if (i < K && j < K) {
+        for (int b = 0; b < slabs; ++b) s += partial[(size_t)b * K * K + i * K + j];
+        if (i == j) s += wd;
+        if (out64) out64[i * K + j] = s;
+    }
     if (outT) outT[t] = (T)s;
 }
 
@@ -103,14 +113,52 @@ template <typename T> struct AlsArgs {
     const int32_t *indices;
     const int32_t *order;       // rows to solve, heaviest first
     int32_t n_solve;
-    T *X;                       // [rows, ldx]  solved in place (warm start = current content)
-    const T *Y;                 // [n, ldy]
-    const T *G;                 // [K, K]  Y^T Y + wd I
-    int32_t K, ldx, ldy, stage_rows, max_iter;
+    T *X;                       // [rows, ld]  solved in place (warm start = current content)
+    const T *Y;                 // [n, ld]
+    const T *G;                 // [ld, ld]  Y^T Y + wd I, zero padded
+    int32_t ld, stage_rows, max_iter;
     T weight, tol2;
     int32_t *queue;             // work-queue head (zeroed before launch)
     unsigned long long *stats;  // [0] CG iterations summed over rows, [1] rows that hit max_iter (may be NULL)
 };
+
+// VW contiguous elements, naturally aligned (VW * sizeof(T) up to 32 bytes)
+template <int VW> __device__ __forceinline__ void ld_vec(const float *p, float (&v)[VW]) {
+    if constexpr (VW == 4) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else if constexpr (VW == 2) { const float2 t = *reinterpret_cast<const float2 *>(p); v[0] = t.x; v[1] = t.y; }
+    else v[0] = *p;
+}
+template <int VW> __device__ __forceinline__ void ld_vec(const double *p, double (&v)[VW]) {
+    if constexpr (VW == 4) {
+        const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else if constexpr (VW == 2) { const double2 t = *reinterpret_cast<const double2 *>(p); v[0] = t.x; v[1] = t.y; }
+    else v[0] = *p;
+}
+template <int VW> __device__ __forceinline__ void ldg_vec(const float *p, float (&v)[VW]) {
+    if constexpr (VW == 4) { const float4 t = __ldg(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else if constexpr (VW == 2) { const float2 t = __ldg(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y; }
+    else v[0] = __ldg(p);
+}
+template <int VW> __device__ __forceinline__ void ldg_vec(const double *p, double (&v)[VW]) {
+    if constexpr (VW == 4) {
+        const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p + 2));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else if constexpr (VW == 2) { const double2 t = __ldg(reinterpret_cast<const double2 *>(p)); v[0] = t.x; v[1] = t.y; }
+    else v[0] = __ldg(p);
+}
+template <int VW> __device__ __forceinline__ void st_vec(float *p, const float (&v)[VW]) {
+    if constexpr (VW == 4) *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else if constexpr (VW == 2) *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+    else *p = v[0];
+}
+template <int VW> __device__ __forceinline__ void st_vec(double *p, const double (&v)[VW]) {
+    if constexpr (VW == 4) {
+        *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2 *>(p + 2) = make_double2(v[2], v[3]);
+    } else if constexpr (VW == 2) *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+    else *p = v[0];
+}
 
 template <typename T> __device__ __forceinline__ T warp_allsum(T v) {
 #pragma unroll
@@ -118,68 +166,47 @@ template <typename T> __device__ __forceinline__ T warp_allsum(T v) {
     return v;
 }
 
-template <typename T> __device__ __forceinline__ T block_sum128(T v, T *red) {   // 4 warps; red[4]
-    v = warp_allsum(v);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    const T s = (red[0] + red[1]) + (red[2] + red[3]);
-    __syncthreads();
-    return s;
+// Sums of four per-lane partials over the warp, each returned to every lane: 10 shuffles instead of 20.
+template <typename T>
+__device__ __forceinline__ void warp_allsum4(T &d0, T &d1, T &d2, T &d3, int lane) {
+    const bool hi16 = lane & 16, hi8 = lane & 8;
+    T k0 = (hi16 ? d1 : d0) + __shfl_xor_sync(0xffffffffu, hi16 ? d0 : d1, 16);   // lanes<16: d0, lanes>=16: d1
+    T k1 = (hi16 ? d3 : d2) + __shfl_xor_sync(0xffffffffu, hi16 ? d2 : d3, 16);   // lanes<16: d2, lanes>=16: d3
+    T k = (hi8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8);       // (bit4,bit3): 00 d0, 01 d2, 10 d1, 11 d3
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    d0 = __shfl_sync(0xffffffffu, k, 0);
+    d2 = __shfl_sync(0xffffffffu, k, 8);
+    d1 = __shfl_sync(0xffffffffu, k, 16);
+    d3 = __shfl_sync(0xffffffffu, k, 24);
 }
 
-template <typename T, int M>          // M = ceil(K / 32): elements of a K-vector per lane
+constexpr int CG_VEC = 128;           // capacity of the shared K-vectors (ld <= 128)
+
+template <typename T, int VW>         // VW = elements of a K-vector per lane (1: ld<=32, 2: ld<=64, 4: ld<=128)
 __global__ void __launch_bounds__(128) als_cg_kernel(const AlsArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int KP = 32 * M;
-    T *p_s = reinterpret_cast<T *>(smem_raw);     // [KP]      search direction, readable by all warps
-    T *part = p_s + KP;                           // [4][KP]   per-warp partial sums
-    T *red = part + 4 * KP;                       // [4]
-    T *Ys = red + 4;                              // [stage_rows][K]
+    T *p_s = reinterpret_cast<T *>(smem_raw);     // [CG_VEC]     search direction, readable by all warps
+    T *part = p_s + CG_VEC;                       // [4][CG_VEC]  per-warp partial A p
+    T *red = part + 4 * CG_VEC;                   // [2][4]       block reductions, double buffered
+    T *Ys = red + 8;                              // [stage_rows][ld]
     __shared__ int row_slot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = a.K;
-    const bool own = tid < K;                     // thread k owns element k of x, r, p (K <= 128)
+    const int ld = a.ld;
+    const int kq = lane * VW;                     // this lane's slice of every K-vector
+    const bool lane_on = kq < ld;
+    const bool own = tid < ld;                    // thread k owns element k of x, r, p
+    const int jn = (ld + 3) >> 2, j0 = warp * jn, j1 = (j0 + jn < ld) ? j0 + jn : ld;   // this warp's rows of G
+    int flip = 0;
 
-    // A v for the vector currently in p_s; returns element `tid`.  Ends with every thread past the last barrier.
-    auto apply = [&](int64_t lo, int nnz, int ns) -> T {
-        T ps[M], acc[M];
-#pragma unroll
-        for (int m = 0; m < M; ++m) { ps[m] = p_s[lane + 32 * m]; acc[m] = T(0); }
-        for (int i = warp; i < nnz; i += 4) {
-            T yv[M];
-            if (i < ns) {
-#pragma unroll
-                for (int m = 0; m < M; ++m) { const int k = lane + 32 * m; yv[m] = k < K ? Ys[i * K + k] : T(0); }
-            } else {
-                const T *y = a.Y + (size_t)__ldg(a.indices + lo + i) * a.ldy;
-#pragma unroll
-                for (int m = 0; m < M; ++m) { const int k = lane + 32 * m; yv[m] = k < K ? __ldg(y + k) : T(0); }
-            }
-            T t = T(0);
-#pragma unroll
-            for (int m = 0; m < M; ++m) t += yv[m] * ps[m];
-            t = warp_allsum(t);
-#pragma unroll
-            for (int m = 0; m < M; ++m) acc[m] += t * yv[m];
-        }
-#pragma unroll
-        for (int m = 0; m < M; ++m) part[warp * KP + lane + 32 * m] = acc[m];
-        T gp = T(0);
-        if (own) {
-            T g0 = T(0), g1 = T(0);
-            int j = 0;
-            for (; j + 1 < K; j += 2) {
-                g0 += __ldg(a.G + (size_t)j * K + tid) * p_s[j];
-                g1 += __ldg(a.G + (size_t)(j + 1) * K + tid) * p_s[j + 1];
-            }
-            if (j < K) g0 += __ldg(a.G + (size_t)j * K + tid) * p_s[j];
-            gp = g0 + g1;
-        }
+    auto block_sum = [&](T v) -> T {
+        v = warp_allsum(v);
+        if (lane == 0) red[flip * 4 + warp] = v;
         __syncthreads();
-        T out = T(0);
-        if (own) out = gp + (a.weight - T(1)) * ((part[tid] + part[KP + tid]) + (part[2 * KP + tid] + part[3 * KP + tid]));
-        __syncthreads();
-        return out;
+        const T s = (red[flip * 4] + red[flip * 4 + 1]) + (red[flip * 4 + 2] + red[flip * 4 + 3]);
+        flip ^= 1;
+        return s;
     };
 
     for (;;) {
@@ -191,55 +218,98 @@ __global__ void __launch_bounds__(128) als_cg_kernel(const AlsArgs<T> a) {
         const int r = a.order[slot];
         const int64_t lo = a.indptr[r];
         const int nnz = (int)(a.indptr[r + 1] - lo);
-        T *xr = a.X + (size_t)r * a.ldx;
+        T *xr = a.X + (size_t)r * ld;
         if (nnz == 0) {                                                        // wmf.pyx:154-156
-            if (tid < a.ldx) xr[tid] = T(0);
+            if (own) xr[tid] = T(0);
             continue;
         }
         const int ns = nnz < a.stage_rows ? nnz : a.stage_rows;
+        const int32_t *idx = a.indices + lo;
+
+        auto load_item = [&](int i, T (&v)[VW]) {                             // item vector slice, zeros past the row
+#pragma unroll
+            for (int e = 0; e < VW; ++e) v[e] = T(0);
+            if (i < nnz && lane_on) {
+                if (i < ns) ld_vec<VW>(Ys + i * ld + kq, v);
+                else ldg_vec<VW>(a.Y + (size_t)__ldg(idx + i) * ld + kq, v);
+            }
+        };
+
+        // A v for the vector in p_s; returns element `tid` (0 for tid >= ld).  One barrier inside.
+        auto apply = [&]() -> T {
+            T ps[VW], acc[VW];
+#pragma unroll
+            for (int e = 0; e < VW; ++e) { ps[e] = T(0); acc[e] = T(0); }
+            if (lane_on) ld_vec<VW>(p_s + kq, ps);
+            for (int i = warp; i < nnz; i += 16) {                             // this warp: items warp, warp+4, ...
+                T y0[VW], y1[VW], y2[VW], y3[VW];
+                load_item(i, y0); load_item(i + 4, y1); load_item(i + 8, y2); load_item(i + 12, y3);
+                T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
+#pragma unroll
+                for (int e = 0; e < VW; ++e) { d0 += y0[e] * ps[e]; d1 += y1[e] * ps[e]; d2 += y2[e] * ps[e]; d3 += y3[e] * ps[e]; }
+                warp_allsum4(d0, d1, d2, d3, lane);
+#pragma unroll
+                for (int e = 0; e < VW; ++e) acc[e] += (d0 * y0[e] + d1 * y1[e]) + (d2 * y2[e] + d3 * y3[e]);
+            }
+            const T wm1 = a.weight - T(1);
+#pragma unroll
+            for (int e = 0; e < VW; ++e) acc[e] *= wm1;
+            if (lane_on) {
+                const T *g = a.G + (size_t)j0 * ld + kq;
+#pragma unroll 4
+                for (int j = j0; j < j1; ++j, g += ld) {                       // + rows [j0, j1) of G p
+                    T gv[VW];
+                    ldg_vec<VW>(g, gv);
+                    const T pj = p_s[j];
+#pragma unroll
+                    for (int e = 0; e < VW; ++e) acc[e] += gv[e] * pj;
+                }
+                st_vec<VW>(part + warp * CG_VEC + kq, acc);
+            }
+            __syncthreads();
+            return own ? (part[tid] + part[CG_VEC + tid]) + (part[2 * CG_VEC + tid] + part[3 * CG_VEC + tid]) : T(0);
+        };
 
         // stage the row's item vectors and accumulate b = w * sum y_i (wmf.pyx:163)
-        T bacc[M];
+        {
+            T bacc[VW];
 #pragma unroll
-        for (int m = 0; m < M; ++m) bacc[m] = T(0);
-        for (int i = warp; i < nnz; i += 4) {
-            const T *y = a.Y + (size_t)__ldg(a.indices + lo + i) * a.ldy;
+            for (int e = 0; e < VW; ++e) bacc[e] = T(0);
+            if (lane_on)
+                for (int i = warp; i < nnz; i += 4) {
+                    T v[VW];
+                    ldg_vec<VW>(a.Y + (size_t)__ldg(idx + i) * ld + kq, v);
 #pragma unroll
-            for (int m = 0; m < M; ++m) {
-                const int k = lane + 32 * m;
-                const T v = k < K ? __ldg(y + k) : T(0);
-                bacc[m] += v;
-                if (i < ns && k < K) Ys[i * K + k] = v;
-            }
+                    for (int e = 0; e < VW; ++e) bacc[e] += v[e];
+                    if (i < ns) st_vec<VW>(Ys + i * ld + kq, v);
+                }
+            if (lane_on) st_vec<VW>(part + warp * CG_VEC + kq, bacc);
         }
-#pragma unroll
-        for (int m = 0; m < M; ++m) part[warp * KP + lane + 32 * m] = bacc[m];
         __syncthreads();
         T b = T(0), x = T(0);
         if (own) {
-            b = a.weight * ((part[tid] + part[KP + tid]) + (part[2 * KP + tid] + part[3 * KP + tid]));
+            b = a.weight * ((part[tid] + part[CG_VEC + tid]) + (part[2 * CG_VEC + tid] + part[3 * CG_VEC + tid]));
             x = xr[tid];                                                        // warm start
+            p_s[tid] = x;
         }
-        if (tid < KP) p_s[tid] = own ? x : T(0);
-        __syncthreads();
-        const T bb = block_sum128(b * b, red);
+        const T bb = block_sum(b * b);                                          // barrier: p_s, Ys and part are settled
         unsigned iters = 0;
         bool stalled = false;
         if (bb > T(0)) {
-            T res = b - apply(lo, nnz, ns);                                     // r0 = b - A x0
+            T res = b - apply();                                                // r0 = b - A x0
             T p = res;
-            T rs = block_sum128(res * res, red);
+            T rs = block_sum(res * res);
             while (rs > a.tol2 * bb) {
                 if ((int)iters >= a.max_iter) { stalled = true; break; }
-                if (tid < KP) p_s[tid] = own ? p : T(0);
+                if (own) p_s[tid] = p;
                 __syncthreads();
-                const T Ap = apply(lo, nnz, ns);
-                const T pAp = block_sum128(p * Ap, red);
+                const T Ap = apply();
+                const T pAp = block_sum(p * Ap);
                 if (!(pAp > T(0))) { stalled = true; break; }
                 const T alpha = rs / pAp;
                 x += alpha * p;
                 res -= alpha * Ap;
-                const T rs_new = block_sum128(res * res, red);
+                const T rs_new = block_sum(res * res);
                 p = res + (rs_new / rs) * p;
                 rs = rs_new;
                 ++iters;
@@ -265,15 +335,14 @@ template <typename T> static int gram_impl(const T *Y, int64_t n, int K, int ld,
         else gram_partial_kernel<T, 8><<<slabs, 256, 0, st>>>(Y, n, K, ld, partial);
         CYMF_LAUNCHED();
     }
-    gram_finish_kernel<T><<<(K * K + 255) / 256, 256, 0, st>>>(partial, slabs, K, add_wd ? wd : 0.0, out64, outT);
+    gram_finish_kernel<T><<<(ld * ld + 255) / 256, 256, 0, st>>>(partial, slabs, K, ld, add_wd ? wd : 0.0, out64, outT);
     CYMF_LAUNCHED();
     return 0;
 }
 
-template <typename T, int M> static int launch_cg(const AlsArgs<T> &a, cudaStream_t st) {
-    constexpr int KP = 32 * M;
-    const size_t smem = sizeof(T) * ((size_t)5 * KP + 4 + (size_t)a.stage_rows * a.K);
-    auto kern = als_cg_kernel<T, M>;
+template <typename T, int VW> static int launch_cg(const AlsArgs<T> &a, cudaStream_t st) {
+    const size_t smem = sizeof(T) * ((size_t)5 * CG_VEC + 8 + (size_t)a.stage_rows * a.ld);
+    auto kern = als_cg_kernel<T, VW>;
     if (smem > 48 * 1024) CYMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CYMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
@@ -288,9 +357,8 @@ template <typename T, int M> static int launch_cg(const AlsArgs<T> &a, cudaStrea
 
 template <typename T> static int cg_impl(AlsArgs<T> a, cudaStream_t st) {
     CYMF_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(int32_t), st));
-    if (a.K <= 32) return launch_cg<T, 1>(a, st);
-    if (a.K <= 64) return launch_cg<T, 2>(a, st);
-    if (a.K <= 96) return launch_cg<T, 3>(a, st);
+    if (a.ld <= 32) return launch_cg<T, 1>(a, st);
+    if (a.ld <= 64) return launch_cg<T, 2>(a, st);
     return launch_cg<T, 4>(a, st);
 }
 
@@ -306,7 +374,8 @@ extern "C" int cymf_gram_dev(const void *Y, int dtype, int64_t n, int32_t K, int
                              int add_weight_decay, double *workspace, int64_t workspace_doubles,
                              double *out_f64, void *out_native, void *stream) {
     CYMF_REQUIRE(Y && workspace && (out_f64 || out_native), "null pointer");
-    CYMF_REQUIRE(n >= 0 && K > 0 && K <= 128 && ld >= K, "bad shape (WMF supports num_components <= 128)");
+    CYMF_REQUIRE(n >= 0 && K > 0 && K <= 128 && ld >= K && ld % 4 == 0 && ld <= 128,
+                 "bad shape (WMF supports num_components <= 128, ld a multiple of 4)");
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == CYMF_F32)
         return gram_impl<float>((const float *)Y, n, K, ld, weight_decay, add_weight_decay, workspace, workspace_doubles,
@@ -318,49 +387,50 @@ extern "C" int cymf_gram_dev(const void *Y, int dtype, int64_t n, int32_t K, int
     return CYMF_EINVAL;
 }
 
-// out_native[t] = (T)(in_f64[t] + wd on the diagonal): finishes a Gram matrix that was all-reduced in f64
-extern "C" int cymf_gram_finalize_dev(const double *in_f64, int dtype, int32_t K, double weight_decay, void *out_native,
-                                      void *stream) {
-    CYMF_REQUIRE(in_f64 && out_native && K > 0 && K <= 128, "bad argument");
+// out_native = [ld, ld] zero-padded copy of (in_f64 [K, K] + wd on the diagonal): finishes a Gram matrix that was
+// all-reduced in f64
+extern "C" int cymf_gram_finalize_dev(const double *in_f64, int dtype, int32_t K, int32_t ld, double weight_decay,
+                                      void *out_native, void *stream) {
+    CYMF_REQUIRE(in_f64 && out_native && K > 0 && K <= 128 && ld >= K && ld <= 128, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == CYMF_F32)
-        gram_finish_kernel<float><<<(K * K + 255) / 256, 256, 0, st>>>(in_f64, 1, K, weight_decay, nullptr, (float *)out_native);
+        gram_finish_kernel<float><<<(ld * ld + 255) / 256, 256, 0, st>>>(in_f64, 1, K, ld, weight_decay, nullptr,
+                                                                         (float *)out_native);
     else
-        gram_finish_kernel<double><<<(K * K + 255) / 256, 256, 0, st>>>(in_f64, 1, K, weight_decay, nullptr, (double *)out_native);
+        gram_finish_kernel<double><<<(ld * ld + 255) / 256, 256, 0, st>>>(in_f64, 1, K, ld, weight_decay, nullptr,
+                                                                          (double *)out_native);
     CYMF_LAUNCHED();
     return 0;
 }
 
 extern "C" int cymf_als_cg_dev(const int64_t *indptr, const int32_t *indices, const int32_t *order, int32_t n_solve,
-                               void *X, const void *Y, const void *G, int dtype, int32_t K, int32_t ldx, int32_t ldy,
+                               void *X, const void *Y, const void *G, int dtype, int32_t K, int32_t ld,
                                double weight, double cg_tol, int32_t cg_max_iter, int32_t stage_rows,
                                int32_t *queue, unsigned long long *stats, void *stream) {
     CYMF_REQUIRE(indptr && indices && order && X && Y && G && queue, "null pointer");
-    CYMF_REQUIRE(K > 0 && K <= 128 && ldx >= K && ldy >= K && ldx <= 128, "bad shape (WMF supports num_components <= 128)");
+    CYMF_REQUIRE(K > 0 && K <= 128 && ld >= K && ld % 4 == 0 && ld <= 128,
+                 "bad shape (WMF supports num_components <= 128, ld a multiple of 4)");
     CYMF_REQUIRE(cg_tol > 0 && cg_max_iter > 0, "bad CG parameters");
     if (n_solve <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t es = dtype == CYMF_F32 ? 4 : 8;
     if (stage_rows <= 0) {                       // auto: ~32 KB of staged item vectors per CTA
-        stage_rows = (int32_t)(32 * 1024 / (es * K));
+        stage_rows = (int32_t)(32 * 1024 / (es * ld));
         if (stage_rows < 8) stage_rows = 8;
     }
     if (dtype == CYMF_F32) {
-        AlsArgs<float> a{indptr, indices, order, n_solve, (float *)X, (const float *)Y, (const float *)G, K, ldx, ldy,
+        AlsArgs<float> a{indptr, indices, order, n_solve, (float *)X, (const float *)Y, (const float *)G, ld,
                          stage_rows, cg_max_iter, (float)weight, (float)(cg_tol * cg_tol), queue, stats};
         return cg_impl<float>(a, st);
     }
     if (dtype == CYMF_F64) {
-        AlsArgs<double> a{indptr, indices, order, n_solve, (double *)X, (const double *)Y, (const double *)G, K, ldx, ldy,
+        AlsArgs<double> a{indptr, indices, order, n_solve, (double *)X, (const double *)Y, (const double *)G, ld,
                           stage_rows, cg_max_iter, weight, cg_tol * cg_tol, queue, stats};
         return cg_impl<double>(a, st);
     }
     set_error("als: unknown dtype %d", dtype);
     return CYMF_EINVAL;
 }
-
-#include <algorithm>
-#include <vector>
 
 extern "C" int cymf_als_half_host(const int32_t *indptr, const int32_t *indices, double *X, const double *Y,
                                   int64_t rows, int64_t n, int32_t K, double weight_decay, double weight,
@@ -397,7 +467,7 @@ extern "C" int cymf_als_half_host(const int32_t *indptr, const int32_t *indices,
     CYMF_TRY(mem.get(&g64, (size_t)K * K * 8));
     CYMF_TRY(mem.get((char **)&dX, (size_t)rows * ld * es));
     CYMF_TRY(mem.get((char **)&dY, (size_t)n * ld * es));
-    CYMF_TRY(mem.get((char **)&dG, (size_t)K * K * es));
+    CYMF_TRY(mem.get((char **)&dG, (size_t)ld * ld * es));
     CYMF_TRY(mem.get(&d_ip, ((size_t)rows + 1) * 8));
     CYMF_TRY(mem.get(&d_ix, (size_t)nnz * 4));
     CYMF_TRY(mem.get(&d_order, (size_t)rows * 4));
@@ -412,7 +482,7 @@ extern "C" int cymf_als_half_host(const int32_t *indptr, const int32_t *indices,
     CYMF_CUDA(cudaMemcpyAsync(d_order, order.data(), (size_t)rows * 4, cudaMemcpyHostToDevice, st));
     CYMF_CUDA(cudaMemsetAsync(d_stats, 0, 16, st));
     CYMF_TRY(cymf_gram_dev(dY, dtype, n, K, ld, weight_decay, 1, ws, wsn, g64, dG, st));
-    CYMF_TRY(cymf_als_cg_dev(d_ip, d_ix, d_order, (int32_t)rows, dX, dY, dG, dtype, K, ld, ld, weight, cg_tol,
+    CYMF_TRY(cymf_als_cg_dev(d_ip, d_ix, d_order, (int32_t)rows, dX, dY, dG, dtype, K, ld, weight, cg_tol,
                              cg_max_iter, 0, d_queue, d_stats, st));
     CYMF_TRY(cymf_unpack_rows_dev(dX, stage, dtype, rows, K, ld, st));
     CYMF_CUDA(cudaMemcpyAsync(X, stage, (size_t)rows * K * 8, cudaMemcpyDeviceToHost, st));

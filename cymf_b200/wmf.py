@@ -212,7 +212,7 @@ class AlsSession(object):
             nws = int(self._L.cymf_gram_workspace_doubles(max(Up, Ip), K))
             self.ws = torch.empty(max(nws, 1), dtype=torch.float64, device=dev)
             self.g64 = torch.empty(K * K, dtype=torch.float64, device=dev)
-            self.G = torch.empty(K * K, dtype=tdt, device=dev)
+            self.G = torch.empty(ld * ld, dtype=tdt, device=dev)       # [ld, ld], zero padded
             self.queue = torch.zeros(1, dtype=torch.int32, device=dev)
             self.d_stats = torch.zeros(2, dtype=torch.int64, device=dev)
         self.epochs_done = 0
@@ -238,13 +238,13 @@ class AlsSession(object):
             _lib.check(L.cymf_gram_dev(_lib.ptr(y_blk), self.dtype, Ry, K, ld, self.wd, 0, _lib.ptr(self.ws),
                                        self.ws.numel(), _lib.ptr(self.g64), None, stream))
             self.dist.all_reduce(self.g64)
-            _lib.check(L.cymf_gram_finalize_dev(_lib.ptr(self.g64), self.dtype, K, self.wd, _lib.ptr(self.G), stream))
+            _lib.check(L.cymf_gram_finalize_dev(_lib.ptr(self.g64), self.dtype, K, ld, self.wd, _lib.ptr(self.G), stream))
         else:
             _lib.check(L.cymf_gram_dev(_lib.ptr(Y_full), self.dtype, Y_full.shape[0], K, ld, self.wd, 1,
                                        _lib.ptr(self.ws), self.ws.numel(), _lib.ptr(self.g64), _lib.ptr(self.G), stream))
         x_blk = X_full[self.rank * R:(self.rank + 1) * R]
         _lib.check(L.cymf_als_cg_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order), R, _lib.ptr(x_blk),
-                                     _lib.ptr(Y_full), _lib.ptr(self.G), self.dtype, K, ld, ld, self.weight, self.cg_tol,
+                                     _lib.ptr(Y_full), _lib.ptr(self.G), self.dtype, K, ld, self.weight, self.cg_tol,
                                      self.cg_max_iter, self.stage_rows, _lib.ptr(self.queue), _lib.ptr(self.d_stats),
                                      stream))
         if self.dist:

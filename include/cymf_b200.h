@@ -142,15 +142,16 @@ int cymf_glove_fit_host(const int32_t *central, const int32_t *context, const do
 /* ---- WMF ALS (cymf/wmf.pyx:136-174, cymf/linalg.pyx:144-163) ------------------------------------------- */
 /* G = Y^T Y (+ weight_decay * I when add_weight_decay != 0), wmf.pyx:142-143.  Y is [n, ld] of `dtype`.
  * `workspace` needs cymf_gram_workspace_doubles(n, K) doubles (per-slab partials, reduced in a fixed order so
- * the result is deterministic).  out_f64 (K*K doubles) and/or out_native (K*K of `dtype`) receive the result.
+ * the result is deterministic).  out_f64 (dense K*K doubles) and/or out_native ([ld, ld] of `dtype`, zero
+ * padded -- the layout cymf_als_cg_dev reads) receive the result.
  * Multi-GPU: each rank calls this on its own row block with add_weight_decay = 0, all-reduces out_f64 and
  * finishes with cymf_gram_finalize_dev. */
 int64_t cymf_gram_workspace_doubles(int64_t n, int32_t K);
 int cymf_gram_dev(const void *Y, int dtype, int64_t n, int32_t K, int32_t ld, double weight_decay,
                   int add_weight_decay, double *workspace, int64_t workspace_doubles,
                   double *out_f64, void *out_native, void *stream);
-int cymf_gram_finalize_dev(const double *in_f64, int dtype, int32_t K, double weight_decay, void *out_native,
-                           void *stream);
+int cymf_gram_finalize_dev(const double *in_f64, int dtype, int32_t K, int32_t ld, double weight_decay,
+                           void *out_native, void *stream);
 
 /* Solves the rows listed in `order` (n_solve row ids, heaviest first) of
  *     (G + (weight-1) sum_{i in row} y_i y_i^T) x = weight sum_{i in row} y_i            (wmf.pyx:158-168)
@@ -161,7 +162,7 @@ int cymf_gram_finalize_dev(const double *in_f64, int dtype, int32_t K, double we
  * [0] += CG iterations over all rows, [1] += rows that stopped at cg_max_iter (the reference drops dgesv's
  * `info`; this is the equivalent health signal). */
 int cymf_als_cg_dev(const int64_t *indptr, const int32_t *indices, const int32_t *order, int32_t n_solve,
-                    void *X, const void *Y, const void *G, int dtype, int32_t K, int32_t ldx, int32_t ldy,
+                    void *X, const void *Y, const void *G, int dtype, int32_t K, int32_t ld,
                     double weight, double cg_tol, int32_t cg_max_iter, int32_t stage_rows,
                     int32_t *queue, unsigned long long *stats, void *stream);
 
