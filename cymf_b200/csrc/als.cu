@@ -116,6 +116,7 @@ template <typename T> struct AlsArgs {
     T *X;                       // [rows, ld]  solved in place (warm start = current content)
     const T *Y;                 // [n, ld]
     const T *G;                 // [ld, ld]  Y^T Y + wd I, zero padded
+    const T *Ginv;              // [ld, ld]  inverse of G (preconditioner) or NULL
     int32_t ld, stage_rows, max_iter;
     T weight, tol2;
     int32_t *queue;             // work-queue head (zeroed before launch)
@@ -181,33 +182,30 @@ __device__ __forceinline__ void warp_allsum4(T &d0, T &d1, T &d2, T &d3, int lan
     d1 = __shfl_sync(0xffffffffu, k, 16);
     d3 = __shfl_sync(0xffffffffu, k, 24);
 }
-
 constexpr int CG_VEC = 128;           // capacity of the shared K-vectors (ld <= 128)
 
-template <typename T, int VW>         // VW = elements of a K-vector per lane (1: ld<=32, 2: ld<=64, 4: ld<=128)
-__global__ void __launch_bounds__(128) als_cg_kernel(const AlsArgs<T> a) {
+// NW warps cooperate on one row.  VW = elements of a K-vector per lane (1: ld<=32, 2: ld<=64, 4: ld<=128).
+template <typename T, int VW, int NW>
+__global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *p_s = reinterpret_cast<T *>(smem_raw);     // [CG_VEC]     search direction, readable by all warps
-    T *part = p_s + CG_VEC;                       // [4][CG_VEC]  per-warp partial A p
-    T *red = part + 4 * CG_VEC;                   // [2][4]       block reductions, double buffered
-    T *Ys = red + 8;                              // [stage_rows][ld]
+    T *const p_s = reinterpret_cast<T *>(smem_raw);     // [CG_VEC]      search direction, readable by all warps
+    T *const part = p_s + CG_VEC;                       // [NW][CG_VEC]  per-warp partial A p
+    T *const red = part + NW * CG_VEC;                  // [2][2 NW]     block reductions, double buffered
+    T *const Ys = red + 4 * NW;                         // [stage_rows][ld]
     __shared__ int row_slot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = a.ld;
-    const int kq = lane * VW;                     // this lane's slice of every K-vector
+    const int kq = lane * VW;                           // this lane's slice of every K-vector
     const bool lane_on = kq < ld;
-    const bool own = tid < ld;                    // thread k owns element k of x, r, p
-    const int jn = (ld + 3) >> 2, j0 = warp * jn, j1 = (j0 + jn < ld) ? j0 + jn : ld;   // this warp's rows of G
+    const bool own = tid < ld;                          // thread k owns element k of x, r, p
+    const int jn = (ld + NW - 1) / NW, j0 = warp * jn, j1 = (j0 + jn < ld) ? j0 + jn : ld;   // this warp's rows of G
+    const T wm1 = a.weight - T(1);
+    const T *const Gw = a.G + (size_t)j0 * ld + kq;
+    const bool pre = a.Ginv != nullptr;                 // G^-1-preconditioned CG
+    const T *const Giw = pre ? a.Ginv + (size_t)j0 * ld + kq : nullptr;
+    const T *const Yq = a.Y + kq;
+    const int stage_rows = a.stage_rows;
     int flip = 0;
-
-    auto block_sum = [&](T v) -> T {
-        v = warp_allsum(v);
-        if (lane == 0) red[flip * 4 + warp] = v;
-        __syncthreads();
-        const T s = (red[flip * 4] + red[flip * 4 + 1]) + (red[flip * 4 + 2] + red[flip * 4 + 3]);
-        flip ^= 1;
-        return s;
-    };
 
     for (;;) {
         if (tid == 0) row_slot = atomicAdd(a.queue, 1);
@@ -218,100 +216,204 @@ __global__ void __launch_bounds__(128) als_cg_kernel(const AlsArgs<T> a) {
         const int r = a.order[slot];
         const int64_t lo = a.indptr[r];
         const int nnz = (int)(a.indptr[r + 1] - lo);
-        T *xr = a.X + (size_t)r * ld;
+        T *const xr = a.X + (size_t)r * ld;
         if (nnz == 0) {                                                        // wmf.pyx:154-156
             if (own) xr[tid] = T(0);
             continue;
         }
-        const int ns = nnz < a.stage_rows ? nnz : a.stage_rows;
-        const int32_t *idx = a.indices + lo;
+        const int ns = nnz < stage_rows ? nnz : stage_rows;
+        const int32_t *const idx = a.indices + lo;
 
-        auto load_item = [&](int i, T (&v)[VW]) {                             // item vector slice, zeros past the row
-#pragma unroll
-            for (int e = 0; e < VW; ++e) v[e] = T(0);
-            if (i < nnz && lane_on) {
-                if (i < ns) ld_vec<VW>(Ys + i * ld + kq, v);
-                else ldg_vec<VW>(a.Y + (size_t)__ldg(idx + i) * ld + kq, v);
-            }
-        };
+#define CYMF_BLOCK_SUM(out, expr)                                                                  \
+    {                                                                                              \
+        T v_ = warp_allsum<T>(expr);                                                               \
+        if (lane == 0) red[flip * 2 * NW + warp] = v_;                                             \
+        __syncthreads();                                                                           \
+        T s_ = T(0);                                                                               \
+        _Pragma("unroll") for (int w_ = 0; w_ < NW; ++w_) s_ += red[flip * 2 * NW + w_];           \
+        flip ^= 1;                                                                                 \
+        out = s_;                                                                                  \
+    }
 
-        // A v for the vector in p_s; returns element `tid` (0 for tid >= ld).  One barrier inside.
-        auto apply = [&]() -> T {
-            T ps[VW], acc[VW];
-#pragma unroll
-            for (int e = 0; e < VW; ++e) { ps[e] = T(0); acc[e] = T(0); }
-            if (lane_on) ld_vec<VW>(p_s + kq, ps);
-            for (int i = warp; i < nnz; i += 16) {                             // this warp: items warp, warp+4, ...
-                T y0[VW], y1[VW], y2[VW], y3[VW];
-                load_item(i, y0); load_item(i + 4, y1); load_item(i + 8, y2); load_item(i + 12, y3);
-                T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
-#pragma unroll
-                for (int e = 0; e < VW; ++e) { d0 += y0[e] * ps[e]; d1 += y1[e] * ps[e]; d2 += y2[e] * ps[e]; d3 += y3[e] * ps[e]; }
-                warp_allsum4(d0, d1, d2, d3, lane);
-#pragma unroll
-                for (int e = 0; e < VW; ++e) acc[e] += (d0 * y0[e] + d1 * y1[e]) + (d2 * y2[e] + d3 * y3[e]);
-            }
-            const T wm1 = a.weight - T(1);
-#pragma unroll
-            for (int e = 0; e < VW; ++e) acc[e] *= wm1;
-            if (lane_on) {
-                const T *g = a.G + (size_t)j0 * ld + kq;
-#pragma unroll 4
-                for (int j = j0; j < j1; ++j, g += ld) {                       // + rows [j0, j1) of G p
-                    T gv[VW];
-                    ldg_vec<VW>(g, gv);
-                    const T pj = p_s[j];
-#pragma unroll
-                    for (int e = 0; e < VW; ++e) acc[e] += gv[e] * pj;
-                }
-                st_vec<VW>(part + warp * CG_VEC + kq, acc);
-            }
-            __syncthreads();
-            return own ? (part[tid] + part[CG_VEC + tid]) + (part[2 * CG_VEC + tid] + part[3 * CG_VEC + tid]) : T(0);
-        };
+#define CYMF_BLOCK_SUM2(out0, out1, expr0, expr1)                                                  \
+    {                                                                                              \
+        T v0_ = warp_allsum<T>(expr0), v1_ = warp_allsum<T>(expr1);                                \
+        if (lane == 0) { red[flip * 2 * NW + warp] = v0_; red[flip * 2 * NW + NW + warp] = v1_; }  \
+        __syncthreads();                                                                           \
+        T s0_ = T(0), s1_ = T(0);                                                                  \
+        _Pragma("unroll") for (int w_ = 0; w_ < NW; ++w_) {                                        \
+            s0_ += red[flip * 2 * NW + w_]; s1_ += red[flip * 2 * NW + NW + w_];                   \
+        }                                                                                          \
+        flip ^= 1;                                                                                 \
+        out0 = s0_; out1 = s1_;                                                                    \
+    }
+
+// z = Ginv * (vector in p_s) -> element `tid` in `out`.  Same row split as the G p term.  One barrier inside.
+#define CYMF_PRECOND(out)                                                                          \
+    {                                                                                              \
+        if (lane_on) {                                                                             \
+            T acc[VW];                                                                             \
+            _Pragma("unroll") for (int e = 0; e < VW; ++e) acc[e] = T(0);                          \
+            const T *g = Giw;                                                                      \
+            _Pragma("unroll 4") for (int j = j0; j < j1; ++j, g += ld) {                           \
+                T gv[VW];                                                                          \
+                ldg_vec<VW>(g, gv);                                                                \
+                const T pj = p_s[j];                                                               \
+                _Pragma("unroll") for (int e = 0; e < VW; ++e) acc[e] += gv[e] * pj;               \
+            }                                                                                      \
+            st_vec<VW>(part + warp * CG_VEC + kq, acc);                                            \
+        }                                                                                          \
+        __syncthreads();                                                                           \
+        T o_ = T(0);                                                                               \
+        if (own) { _Pragma("unroll") for (int w_ = 0; w_ < NW; ++w_) o_ += part[w_ * CG_VEC + tid]; } \
+        out = o_;                                                                                  \
+    }
+
+// A v for the vector in p_s -> element `tid` of the result in `out` (0 for tid >= ld).  One barrier inside.
+// The warp's items are warp, warp+NW, ...; four at a time share one reduction butterfly.
+#define CYMF_APPLY(out)                                                                            \
+    {                                                                                              \
+        T ps[VW], acc[VW];                                                                         \
+        _Pragma("unroll") for (int e = 0; e < VW; ++e) { ps[e] = T(0); acc[e] = T(0); }            \
+        if (lane_on) ld_vec<VW>(p_s + kq, ps);                                                     \
+        int i = warp;                                                                              \
+        for (; i + 3 * NW < ns; i += 4 * NW) {                  /* four staged items */           \
+            T y0[VW], y1[VW], y2[VW], y3[VW];                                                      \
+            _Pragma("unroll") for (int e = 0; e < VW; ++e) { y0[e] = y1[e] = y2[e] = y3[e] = T(0); } \
+            if (lane_on) {                                                                         \
+                const T *s = Ys + i * ld + kq;                                                     \
+                ld_vec<VW>(s, y0); ld_vec<VW>(s + NW * ld, y1);                                    \
+                ld_vec<VW>(s + 2 * NW * ld, y2); ld_vec<VW>(s + 3 * NW * ld, y3);                  \
+            }                                                                                      \
+            T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);                                          \
+            _Pragma("unroll") for (int e = 0; e < VW; ++e) {                                       \
+                d0 += y0[e] * ps[e]; d1 += y1[e] * ps[e]; d2 += y2[e] * ps[e]; d3 += y3[e] * ps[e]; \
+            }                                                                                      \
+            warp_allsum4(d0, d1, d2, d3, lane);                                                    \
+            _Pragma("unroll") for (int e = 0; e < VW; ++e)                                         \
+                acc[e] += (d0 * y0[e] + d1 * y1[e]) + (d2 * y2[e] + d3 * y3[e]);                   \
+        }                                                                                          \
+        for (; i < nnz; i += 4 * NW) {                          /* mixed / streamed / tail items */ \
+            T y0[VW], y1[VW], y2[VW], y3[VW];                                                      \
+            _Pragma("unroll") for (int e = 0; e < VW; ++e) { y0[e] = y1[e] = y2[e] = y3[e] = T(0); } \
+            if (lane_on) {                                                                         \
+                const int i1 = i + NW, i2 = i + 2 * NW, i3 = i + 3 * NW;                           \
+                if (i < ns) ld_vec<VW>(Ys + i * ld + kq, y0);                                      \
+                else ldg_vec<VW>(Yq + (size_t)__ldg(idx + i) * ld, y0);                            \
+                if (i1 < ns) ld_vec<VW>(Ys + i1 * ld + kq, y1);                                    \
+                else if (i1 < nnz) ldg_vec<VW>(Yq + (size_t)__ldg(idx + i1) * ld, y1);             \
+                if (i2 < ns) ld_vec<VW>(Ys + i2 * ld + kq, y2);                                    \
+                else if (i2 < nnz) ldg_vec<VW>(Yq + (size_t)__ldg(idx + i2) * ld, y2);             \
+                if (i3 < ns) ld_vec<VW>(Ys + i3 * ld + kq, y3);                                    \
+                else if (i3 < nnz) ldg_vec<VW>(Yq + (size_t)__ldg(idx + i3) * ld, y3);             \
+            }                                                                                      \
+            T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);                                          \
+            _Pragma("unroll") for (int e = 0; e < VW; ++e) {                                       \
+                d0 += y0[e] * ps[e]; d1 += y1[e] * ps[e]; d2 += y2[e] * ps[e]; d3 += y3[e] * ps[e]; \
+            }                                                                                      \
+            warp_allsum4(d0, d1, d2, d3, lane);                                                    \
+            _Pragma("unroll") for (int e = 0; e < VW; ++e)                                         \
+                acc[e] += (d0 * y0[e] + d1 * y1[e]) + (d2 * y2[e] + d3 * y3[e]);                   \
+        }                                                                                          \
+        _Pragma("unroll") for (int e = 0; e < VW; ++e) acc[e] *= wm1;                              \
+        if (lane_on) {                                                                             \
+            const T *g = Gw;                                                                       \
+            _Pragma("unroll 4") for (int j = j0; j < j1; ++j, g += ld) {   /* + rows [j0, j1) of G p */ \
+                T gv[VW];                                                                          \
+                ldg_vec<VW>(g, gv);                                                                \
+                const T pj = p_s[j];                                                               \
+                _Pragma("unroll") for (int e = 0; e < VW; ++e) acc[e] += gv[e] * pj;               \
+            }                                                                                      \
+            st_vec<VW>(part + warp * CG_VEC + kq, acc);                                            \
+        }                                                                                          \
+        __syncthreads();                                                                           \
+        T o_ = T(0);                                                                               \
+        if (own) { _Pragma("unroll") for (int w_ = 0; w_ < NW; ++w_) o_ += part[w_ * CG_VEC + tid]; } \
+        out = o_;                                                                                  \
+    }
 
         // stage the row's item vectors and accumulate b = w * sum y_i (wmf.pyx:163)
         {
             T bacc[VW];
 #pragma unroll
             for (int e = 0; e < VW; ++e) bacc[e] = T(0);
-            if (lane_on)
-                for (int i = warp; i < nnz; i += 4) {
-                    T v[VW];
-                    ldg_vec<VW>(a.Y + (size_t)__ldg(idx + i) * ld + kq, v);
+            if (lane_on) {
+                int i = warp;
+                for (; i + NW < nnz; i += 2 * NW) {                            // two gathers in flight
+                    T v0[VW], v1[VW];
+                    ldg_vec<VW>(Yq + (size_t)__ldg(idx + i) * ld, v0);
+                    ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + NW) * ld, v1);
 #pragma unroll
-                    for (int e = 0; e < VW; ++e) bacc[e] += v[e];
-                    if (i < ns) st_vec<VW>(Ys + i * ld + kq, v);
+                    for (int e = 0; e < VW; ++e) bacc[e] += v0[e] + v1[e];
+                    if (i < ns) st_vec<VW>(Ys + i * ld + kq, v0);
+                    if (i + NW < ns) st_vec<VW>(Ys + (i + NW) * ld + kq, v1);
                 }
-            if (lane_on) st_vec<VW>(part + warp * CG_VEC + kq, bacc);
+                if (i < nnz) {
+                    T v0[VW];
+                    ldg_vec<VW>(Yq + (size_t)__ldg(idx + i) * ld, v0);
+#pragma unroll
+                    for (int e = 0; e < VW; ++e) bacc[e] += v0[e];
+                    if (i < ns) st_vec<VW>(Ys + i * ld + kq, v0);
+                }
+                st_vec<VW>(part + warp * CG_VEC + kq, bacc);
+            }
         }
         __syncthreads();
         T b = T(0), x = T(0);
         if (own) {
-            b = a.weight * ((part[tid] + part[CG_VEC + tid]) + (part[2 * CG_VEC + tid] + part[3 * CG_VEC + tid]));
+#pragma unroll
+            for (int w = 0; w < NW; ++w) b += part[w * CG_VEC + tid];
+            b *= a.weight;
             x = xr[tid];                                                        // warm start
             p_s[tid] = x;
         }
-        const T bb = block_sum(b * b);                                          // barrier: p_s, Ys and part are settled
+        T bb;
+        CYMF_BLOCK_SUM(bb, b * b);                                              // barrier: p_s, Ys and part are settled
         unsigned iters = 0;
         bool stalled = false;
         if (bb > T(0)) {
-            T res = b - apply();                                                // r0 = b - A x0
-            T p = res;
-            T rs = block_sum(res * res);
+            T Ax;
+            CYMF_APPLY(Ax);
+            T res = b - Ax;                                                     // r0 = b - A x0
+            T rs, rz;
+            T z = res;
+            if (pre) {                                                          // z = G^-1 r (preconditioner)
+                __syncthreads();
+                if (own) p_s[tid] = res;
+                __syncthreads();
+                CYMF_PRECOND(z);
+                CYMF_BLOCK_SUM2(rs, rz, res * res, res * z);
+            } else {
+                CYMF_BLOCK_SUM(rs, res * res);
+                rz = rs;
+            }
+            T p = z;
             while (rs > a.tol2 * bb) {
                 if ((int)iters >= a.max_iter) { stalled = true; break; }
                 if (own) p_s[tid] = p;
                 __syncthreads();
-                const T Ap = apply();
-                const T pAp = block_sum(p * Ap);
+                T Ap;
+                CYMF_APPLY(Ap);
+                T pAp;
+                CYMF_BLOCK_SUM(pAp, p * Ap);
                 if (!(pAp > T(0))) { stalled = true; break; }
-                const T alpha = rs / pAp;
+                const T alpha = rz / pAp;
                 x += alpha * p;
                 res -= alpha * Ap;
-                const T rs_new = block_sum(res * res);
-                p = res + (rs_new / rs) * p;
+                T rs_new, rz_new;
+                if (pre) {
+                    if (own) p_s[tid] = res;                                    // all reads of p_s are behind a barrier
+                    __syncthreads();
+                    CYMF_PRECOND(z);
+                    CYMF_BLOCK_SUM2(rs_new, rz_new, res * res, res * z);
+                } else {
+                    CYMF_BLOCK_SUM(rs_new, res * res);
+                    rz_new = rs_new;
+                    z = res;
+                }
+                p = z + (rz_new / rz) * p;
                 rs = rs_new;
+                rz = rz_new;
                 ++iters;
             }
         } else {
@@ -322,6 +424,10 @@ __global__ void __launch_bounds__(128) als_cg_kernel(const AlsArgs<T> a) {
             atomicAdd(a.stats, (unsigned long long)iters);
             if (stalled) atomicAdd(a.stats + 1, 1ull);
         }
+#undef CYMF_APPLY
+#undef CYMF_BLOCK_SUM
+#undef CYMF_BLOCK_SUM2
+#undef CYMF_PRECOND
     }
 }
 
@@ -340,26 +446,40 @@ template <typename T> static int gram_impl(const T *Y, int64_t n, int K, int ld,
     return 0;
 }
 
-template <typename T, int VW> static int launch_cg(const AlsArgs<T> &a, cudaStream_t st) {
-    const size_t smem = sizeof(T) * ((size_t)5 * CG_VEC + 8 + (size_t)a.stage_rows * a.ld);
-    auto kern = als_cg_kernel<T, VW>;
+
+template <typename T, int VW, int NW> static int launch_cg(AlsArgs<T> a, int32_t stage_rows, cudaStream_t st) {
+    const size_t fixed = sizeof(T) * ((size_t)(1 + NW) * CG_VEC + 4 * NW);
+    if (stage_rows <= 0) {                       // auto: 8 KB of staged item vectors per warp (32 / 64 / 128 KB per CTA)
+        stage_rows = (int32_t)((size_t)NW * 8 * 1024 / (sizeof(T) * a.ld));
+        if (stage_rows < 8) stage_rows = 8;
+    }
+    a.stage_rows = stage_rows;
+    const size_t smem = fixed + sizeof(T) * (size_t)stage_rows * a.ld;
+    if (smem > 220 * 1024) { set_error("als: stage_rows=%d does not fit shared memory", stage_rows); return CYMF_EINVAL; }
+    auto kern = als_cg_kernel<T, VW, NW>;
     if (smem > 48 * 1024) CYMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CYMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+    CYMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * NW, smem));
     if (per_sm < 1) per_sm = 1;
     int64_t blocks = (int64_t)sm_count() * per_sm;
     if (blocks > a.n_solve) blocks = a.n_solve;
     if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, 128, smem, st>>>(a);
+    kern<<<(unsigned)blocks, 32 * NW, smem, st>>>(a);
     CYMF_LAUNCHED();
     return 0;
 }
 
-template <typename T> static int cg_impl(AlsArgs<T> a, cudaStream_t st) {
+template <typename T, int NW> static int cg_by_width(const AlsArgs<T> &a, int32_t stage_rows, cudaStream_t st) {
+    if (a.ld <= 32) return launch_cg<T, 1, NW>(a, stage_rows, st);
+    if (a.ld <= 64) return launch_cg<T, 2, NW>(a, stage_rows, st);
+    return launch_cg<T, 4, NW>(a, stage_rows, st);
+}
+
+template <typename T> static int cg_impl(const AlsArgs<T> &a, int32_t warps_per_row, int32_t stage_rows, cudaStream_t st) {
     CYMF_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(int32_t), st));
-    if (a.ld <= 32) return launch_cg<T, 1>(a, st);
-    if (a.ld <= 64) return launch_cg<T, 2>(a, st);
-    return launch_cg<T, 4>(a, st);
+    if (warps_per_row >= 16) return cg_by_width<T, 16>(a, stage_rows, st);
+    if (warps_per_row >= 8) return cg_by_width<T, 8>(a, stage_rows, st);
+    return cg_by_width<T, 4>(a, stage_rows, st);
 }
 
 }  // namespace cymf
@@ -403,33 +523,94 @@ extern "C" int cymf_gram_finalize_dev(const double *in_f64, int dtype, int32_t K
     return 0;
 }
 
+// In-place Gauss-Jordan inversion of a symmetric positive definite K x K matrix (f64, one CTA, matrix in shared
+// memory; no pivoting is needed for SPD input).  Output [ld, ld] of T, zero padded.
+template <typename T>
+__global__ void __launch_bounds__(1024) spd_inverse_kernel(const double *__restrict__ A, int K, int ld, double add_diag,
+                                                           T *__restrict__ out) {
+    extern __shared__ double sm[];
+    double *M = sm, *rowk = sm + K * K, *colk = rowk + K;
+    for (int t = threadIdx.x; t < K * K; t += blockDim.x) M[t] = A[t] + ((t / K == t % K) ? add_diag : 0.0);
+    __syncthreads();
+    for (int k = 0; k < K; ++k) {
+        const double piv = M[k * K + k];
+        for (int t = threadIdx.x; t < K; t += blockDim.x) {
+            rowk[t] = (t == k ? 1.0 : M[k * K + t]) / piv;
+            colk[t] = M[t * K + k];
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < K * K; t += blockDim.x) {
+            const int i = t / K, j = t - i * K;
+            if (i == k) M[t] = rowk[j];
+            else M[t] = (j == k ? 0.0 : M[t]) - colk[i] * rowk[j];
+        }
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < ld * ld; t += blockDim.x) {
+        const int i = t / ld, j = t - i * ld;
+        out[t] = (i < K && j < K) ? (T)(0.5 * (M[i * K + j] + M[j * K + i])) : T(0);
+    }
+}
+
+extern "C" int cymf_spd_inverse_dev(const double *A, int32_t K, int32_t ld, double add_diag, int dtype,
+                                    void *out_native, void *stream) {
+    CYMF_REQUIRE(A && out_native && K > 0 && K <= 128 && ld >= K && ld <= 128, "bad argument");
+    const size_t smem = sizeof(double) * ((size_t)K * K + 2 * K);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CYMF_F32) {
+        if (smem > 48 * 1024)
+            CYMF_CUDA(cudaFuncSetAttribute(spd_inverse_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        spd_inverse_kernel<float><<<1, 1024, smem, st>>>(A, K, ld, add_diag, (float *)out_native);
+    } else {
+        if (smem > 48 * 1024)
+            CYMF_CUDA(cudaFuncSetAttribute(spd_inverse_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        spd_inverse_kernel<double><<<1, 1024, smem, st>>>(A, K, ld, add_diag, (double *)out_native);
+    }
+    CYMF_LAUNCHED();
+    return 0;
+}
+
 extern "C" int cymf_als_cg_dev(const int64_t *indptr, const int32_t *indices, const int32_t *order, int32_t n_solve,
-                               void *X, const void *Y, const void *G, int dtype, int32_t K, int32_t ld,
-                               double weight, double cg_tol, int32_t cg_max_iter, int32_t stage_rows,
-                               int32_t *queue, unsigned long long *stats, void *stream) {
+                               void *X, const void *Y, const void *G, const void *Ginv, int dtype, int32_t K, int32_t ld,
+                               double weight, double cg_tol, int32_t cg_max_iter, int32_t warps_per_row,
+                               int32_t stage_rows, int32_t *queue, unsigned long long *stats, void *stream) {
     CYMF_REQUIRE(indptr && indices && order && X && Y && G && queue, "null pointer");
     CYMF_REQUIRE(K > 0 && K <= 128 && ld >= K && ld % 4 == 0 && ld <= 128,
                  "bad shape (WMF supports num_components <= 128, ld a multiple of 4)");
     CYMF_REQUIRE(cg_tol > 0 && cg_max_iter > 0, "bad CG parameters");
     if (n_solve <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t es = dtype == CYMF_F32 ? 4 : 8;
-    if (stage_rows <= 0) {                       // auto: ~32 KB of staged item vectors per CTA
-        stage_rows = (int32_t)(32 * 1024 / (es * ld));
-        if (stage_rows < 8) stage_rows = 8;
-    }
     if (dtype == CYMF_F32) {
-        AlsArgs<float> a{indptr, indices, order, n_solve, (float *)X, (const float *)Y, (const float *)G, ld,
-                         stage_rows, cg_max_iter, (float)weight, (float)(cg_tol * cg_tol), queue, stats};
-        return cg_impl<float>(a, st);
+        AlsArgs<float> a{indptr, indices, order, n_solve, (float *)X, (const float *)Y, (const float *)G,
+                         (const float *)Ginv, ld, 0, cg_max_iter, (float)weight, (float)(cg_tol * cg_tol), queue, stats};
+        return cg_impl<float>(a, warps_per_row, stage_rows, st);
     }
     if (dtype == CYMF_F64) {
-        AlsArgs<double> a{indptr, indices, order, n_solve, (double *)X, (const double *)Y, (const double *)G, ld,
-                          stage_rows, cg_max_iter, weight, cg_tol * cg_tol, queue, stats};
-        return cg_impl<double>(a, st);
+        AlsArgs<double> a{indptr, indices, order, n_solve, (double *)X, (const double *)Y, (const double *)G,
+                          (const double *)Ginv, ld, 0, cg_max_iter, weight, cg_tol * cg_tol, queue, stats};
+        return cg_impl<double>(a, warps_per_row, stage_rows, st);
     }
     set_error("als: unknown dtype %d", dtype);
     return CYMF_EINVAL;
+}
+
+// Rows sorted by decreasing length split into three classes by how many item vectors fit the staging area of a
+// 4-, 8- or 16-warp CTA (8 KB per warp): returns the number of rows for 16 and for 8 warps (the rest take 4).
+extern "C" int cymf_als_row_classes(const int64_t *sorted_lengths_desc, int64_t n, int dtype, int32_t ld,
+                                    int64_t *n_wide16, int64_t *n_wide8) {
+    CYMF_REQUIRE(sorted_lengths_desc && n_wide16 && n_wide8 && n >= 0 && ld > 0, "bad argument");
+    // Measured on B200 (tools/als_tune.py, ml-20m shape, K=128): 4 warps per row win up to a few hundred entries
+    // (137 on average: 22 ms vs 28 ms with 8 and 45 ms with 16 warps), 16 warps win on rows averaging 673 entries
+    // (20 ms vs 22 ms / 30 ms); per-iteration barriers and the 1/NW-th share of G p set the crossover.
+    (void)dtype; (void)ld;
+    const int64_t wide8 = 384, wide16 = 1024;
+    int64_t a = 0, b = 0;
+    while (a < n && sorted_lengths_desc[a] > wide16) ++a;
+    b = a;
+    while (b < n && sorted_lengths_desc[b] > wide8) ++b;
+    *n_wide16 = a;
+    *n_wide8 = b - a;
+    return 0;
 }
 
 extern "C" int cymf_als_half_host(const int32_t *indptr, const int32_t *indices, double *X, const double *Y,
@@ -482,8 +663,20 @@ extern "C" int cymf_als_half_host(const int32_t *indptr, const int32_t *indices,
     CYMF_CUDA(cudaMemcpyAsync(d_order, order.data(), (size_t)rows * 4, cudaMemcpyHostToDevice, st));
     CYMF_CUDA(cudaMemsetAsync(d_stats, 0, 16, st));
     CYMF_TRY(cymf_gram_dev(dY, dtype, n, K, ld, weight_decay, 1, ws, wsn, g64, dG, st));
-    CYMF_TRY(cymf_als_cg_dev(d_ip, d_ix, d_order, (int32_t)rows, dX, dY, dG, dtype, K, ld, weight, cg_tol,
-                             cg_max_iter, 0, d_queue, d_stats, st));
+    void *dGinv = nullptr;                                       // G^-1 preconditioner: ~40 % fewer CG iterations
+    CYMF_TRY(mem.get((char **)&dGinv, (size_t)ld * ld * es));
+    CYMF_TRY(cymf_spd_inverse_dev(g64, K, ld, 0.0, dtype, dGinv, st));
+    {   // heaviest rows with 16 warps per row, medium with 8, the rest with 4
+        std::vector<int64_t> len((size_t)rows);
+        for (int64_t t = 0; t < rows; ++t) len[(size_t)t] = indptr[order[(size_t)t] + 1] - indptr[order[(size_t)t]];
+        int64_t n16 = 0, n8 = 0;
+        CYMF_TRY(cymf_als_row_classes(len.data(), rows, dtype, ld, &n16, &n8));
+        const int64_t start[3] = {0, n16, n16 + n8}, count[3] = {n16, n8, rows - n16 - n8};
+        const int32_t width[3] = {16, 8, 4};
+        for (int c = 0; c < 3; ++c)
+            CYMF_TRY(cymf_als_cg_dev(d_ip, d_ix, d_order + start[c], (int32_t)count[c], dX, dY, dG, dGinv, dtype, K, ld,
+                                     weight, cg_tol, cg_max_iter, width[c], 0, d_queue, d_stats, st));
+    }
     CYMF_TRY(cymf_unpack_rows_dev(dX, stage, dtype, rows, K, ld, st));
     CYMF_CUDA(cudaMemcpyAsync(X, stage, (size_t)rows * K * 8, cudaMemcpyDeviceToHost, st));
     unsigned long long stats[2] = {0, 0};

@@ -171,8 +171,10 @@ class AlsSession(object):
     replicas of W and H in dealt order); `epoch()` = user half sweep + item half sweep (wmf.pyx:111-112)."""
 
     def __init__(self, X, W, H, weight_decay, weight, *, dtype="float32", cg_tol=1e-6, cg_max_iter=128, device=None,
-                 distributed="auto", stage_rows=0):
+                 distributed="auto", stage_rows=0, force_width=0, precondition=True):
         torch = _lib.require_cuda()
+        self.force_width = int(force_width)
+        self.precondition = bool(precondition)
         import torch.distributed as dist
         self._L = _lib.lib()
         self.dist = dist if (distributed in ("auto", True) and dist.is_available() and dist.is_initialized()
@@ -200,6 +202,8 @@ class AlsSession(object):
         blk_i = _relabel(XT, self.slot_i[lo_i:lo_i + self.Ri], new_u, Up)
         self.nnz = int(X.nnz)
         self.block_nnz = (int(blk_u.nnz), int(blk_i.nnz))
+        self.classes_u = self._classes(blk_u)
+        self.classes_i = self._classes(blk_i)
         with torch.cuda.device(dev):
             def up(a, dt):
                 return torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev, non_blocking=True)
@@ -213,6 +217,7 @@ class AlsSession(object):
             self.ws = torch.empty(max(nws, 1), dtype=torch.float64, device=dev)
             self.g64 = torch.empty(K * K, dtype=torch.float64, device=dev)
             self.G = torch.empty(ld * ld, dtype=tdt, device=dev)       # [ld, ld], zero padded
+            self.Ginv = torch.empty(ld * ld, dtype=tdt, device=dev)
             self.queue = torch.zeros(1, dtype=torch.int32, device=dev)
             self.d_stats = torch.zeros(2, dtype=torch.int64, device=dev)
         self.epochs_done = 0
@@ -227,7 +232,18 @@ class AlsSession(object):
         return _lib.upload_factor(dealt, self.dtype, self.dev)
 
     # one half sweep: solve `rows_side` from the fixed side (wmf.pyx:136-174)
-    def _half(self, X_full, R, csr, order, Y_full, Ry):
+    def _classes(self, blk):
+        """(rows solved with 16 warps, with 8, with 4): split of the block's rows (already heaviest first)."""
+        lengths = np.ascontiguousarray(np.diff(blk.indptr), np.int64)
+        if self.force_width:                                   # tuning hook: one CTA width for every row
+            n = int(lengths.shape[0])
+            return {16: (n, 0, 0), 8: (0, n, 0), 4: (0, 0, n)}[self.force_width]
+        n16, n8 = C.c_int64(0), C.c_int64(0)
+        _lib.check(self._L.cymf_als_row_classes(lengths.ctypes.data_as(C.c_void_p), lengths.shape[0], self.dtype,
+                                                self.ld, C.byref(n16), C.byref(n8)))
+        return int(n16.value), int(n8.value), int(lengths.shape[0] - n16.value - n8.value)
+
+    def _half(self, X_full, R, csr, order, Y_full, Ry, classes):
         import torch
         L, K, ld = self._L, self.K, self.ld
         stream = _lib.stream_ptr()
@@ -239,22 +255,34 @@ class AlsSession(object):
                                        self.ws.numel(), _lib.ptr(self.g64), None, stream))
             self.dist.all_reduce(self.g64)
             _lib.check(L.cymf_gram_finalize_dev(_lib.ptr(self.g64), self.dtype, K, ld, self.wd, _lib.ptr(self.G), stream))
+            add_diag = self.wd                                   # g64 holds the all-reduced Y^T Y without wd I
         else:
             _lib.check(L.cymf_gram_dev(_lib.ptr(Y_full), self.dtype, Y_full.shape[0], K, ld, self.wd, 1,
                                        _lib.ptr(self.ws), self.ws.numel(), _lib.ptr(self.g64), _lib.ptr(self.G), stream))
+            add_diag = 0.0
+        ginv = None
+        if self.precondition:                                    # G^-1 as CG preconditioner (f64 Gauss-Jordan, one CTA)
+            _lib.check(L.cymf_spd_inverse_dev(_lib.ptr(self.g64), K, ld, add_diag, self.dtype, _lib.ptr(self.Ginv), stream))
+            ginv = self.Ginv
         x_blk = X_full[self.rank * R:(self.rank + 1) * R]
-        _lib.check(L.cymf_als_cg_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order), R, _lib.ptr(x_blk),
-                                     _lib.ptr(Y_full), _lib.ptr(self.G), self.dtype, K, ld, self.weight, self.cg_tol,
-                                     self.cg_max_iter, self.stage_rows, _lib.ptr(self.queue), _lib.ptr(self.d_stats),
-                                     stream))
+        # rows of the block are sorted heaviest first: 16 warps per row for the longest, then 8, then 4
+        start = 0
+        for width, count in zip((16, 8, 4), classes):
+            if count:
+                _lib.check(L.cymf_als_cg_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order[start:]), count,
+                                             _lib.ptr(x_blk), _lib.ptr(Y_full), _lib.ptr(self.G), _lib.ptr(ginv),
+                                             self.dtype, K, ld,
+                                             self.weight, self.cg_tol, self.cg_max_iter, width, self.stage_rows,
+                                             _lib.ptr(self.queue), _lib.ptr(self.d_stats), stream))
+            start += count
         if self.dist:
             self.dist.all_gather_into_tensor(X_full, x_blk)
 
     def user_half(self):
-        self._half(self.dW, self.Ru, self.csr_u, self.order_u, self.dH, self.Ri)
+        self._half(self.dW, self.Ru, self.csr_u, self.order_u, self.dH, self.Ri, self.classes_u)
 
     def item_half(self):
-        self._half(self.dH, self.Ri, self.csr_i, self.order_i, self.dW, self.Ru)
+        self._half(self.dH, self.Ri, self.csr_i, self.order_i, self.dW, self.Ru, self.classes_i)
 
     def epoch(self):
         import torch

@@ -162,9 +162,22 @@ int cymf_gram_finalize_dev(const double *in_f64, int dtype, int32_t K, int32_t l
  * [0] += CG iterations over all rows, [1] += rows that stopped at cg_max_iter (the reference drops dgesv's
  * `info`; this is the equivalent health signal). */
 int cymf_als_cg_dev(const int64_t *indptr, const int32_t *indices, const int32_t *order, int32_t n_solve,
-                    void *X, const void *Y, const void *G, int dtype, int32_t K, int32_t ld,
-                    double weight, double cg_tol, int32_t cg_max_iter, int32_t stage_rows,
-                    int32_t *queue, unsigned long long *stats, void *stream);
+                    void *X, const void *Y, const void *G, const void *Ginv, int dtype, int32_t K, int32_t ld,
+                    double weight, double cg_tol, int32_t cg_max_iter, int32_t warps_per_row,
+                    int32_t stage_rows, int32_t *queue, unsigned long long *stats, void *stream);
+
+/* Ginv of cymf_als_cg_dev (may be NULL): [ld, ld] inverse of G, used as the CG preconditioner.  The
+ * preconditioned operator is I + (w-1) G^-1 Y_r^T Y_r, whose spectrum is clustered near 1, so rows converge in
+ * roughly half the iterations.  cymf_spd_inverse_dev computes it on the device from the dense f64 K x K matrix
+ * A (+ add_diag on the diagonal) by in-place Gauss-Jordan elimination in f64. */
+int cymf_spd_inverse_dev(const double *A, int32_t K, int32_t ld, double add_diag, int dtype, void *out_native,
+                         void *stream);
+
+/* warps_per_row of cymf_als_cg_dev is 4, 8 or 16 (CTA width per row; each warp brings 8 KB of shared-memory
+ * staging for the row's item vectors).  Given the row lengths in `order` (decreasing), this returns how many
+ * leading rows should be solved with 16 warps and how many following ones with 8; the rest take 4. */
+int cymf_als_row_classes(const int64_t *sorted_lengths_desc, int64_t n, int dtype, int32_t ld,
+                         int64_t *n_wide16, int64_t *n_wide8);
 
 /* Host-buffer form of WMF._als(indptr, indices, X, Y, num_threads): X [rows,K], Y [n,K] dense f64 HOST arrays,
  * host CSR (int32), X solved in place.  dtype selects the device arithmetic (CYMF_F32 / CYMF_F64). */
