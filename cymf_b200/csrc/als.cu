@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
     const bool own = tid < ld;                          // thread k owns element k of x, r, p
     const int jn = (ld + NW - 1) / NW, j0 = warp * jn, j1 = (j0 + jn < ld) ? j0 + jn : ld;   // this warp's rows of G
     const T wm1 = a.weight - T(1);
-    const T *const Gw = a.G + (size_t)j0 * ld + kq;
+    const bool dense = a.G != nullptr;                  // false: factors were transformed so that G = I
+    const T *const Gw = dense ? a.G + (size_t)j0 * ld + kq : nullptr;
     const bool pre = a.Ginv != nullptr;                 // G^-1-preconditioned CG
     const T *const Giw = pre ? a.Ginv + (size_t)j0 * ld + kq : nullptr;
     const T *const Yq = a.Y + kq;
@@ -317,18 +318,23 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
         }                                                                                          \
         _Pragma("unroll") for (int e = 0; e < VW; ++e) acc[e] *= wm1;                              \
         if (lane_on) {                                                                             \
-            const T *g = Gw;                                                                       \
-            _Pragma("unroll 4") for (int j = j0; j < j1; ++j, g += ld) {   /* + rows [j0, j1) of G p */ \
-                T gv[VW];                                                                          \
-                ldg_vec<VW>(g, gv);                                                                \
-                const T pj = p_s[j];                                                               \
-                _Pragma("unroll") for (int e = 0; e < VW; ++e) acc[e] += gv[e] * pj;               \
+            if (dense) {                                                                           \
+                const T *g = Gw;                                                                   \
+                _Pragma("unroll 4") for (int j = j0; j < j1; ++j, g += ld) {  /* + rows [j0, j1) of G p */ \
+                    T gv[VW];                                                                      \
+                    ldg_vec<VW>(g, gv);                                                            \
+                    const T pj = p_s[j];                                                           \
+                    _Pragma("unroll") for (int e = 0; e < VW; ++e) acc[e] += gv[e] * pj;           \
+                }                                                                                  \
             }                                                                                      \
             st_vec<VW>(part + warp * CG_VEC + kq, acc);                                            \
         }                                                                                          \
         __syncthreads();                                                                           \
         T o_ = T(0);                                                                               \
-        if (own) { _Pragma("unroll") for (int w_ = 0; w_ < NW; ++w_) o_ += part[w_ * CG_VEC + tid]; } \
+        if (own) {                                                                                 \
+            _Pragma("unroll") for (int w_ = 0; w_ < NW; ++w_) o_ += part[w_ * CG_VEC + tid];       \
+            if (!dense) o_ += p_s[tid];                /* transformed space: G = I */             \
+        }                                                                                          \
         out = o_;                                                                                  \
     }
 
@@ -552,6 +558,139 @@ __global__ void __launch_bounds__(1024) spd_inverse_kernel(const double *__restr
     }
 }
 
+// Cholesky G = L L^T (f64, one CTA, shared memory) and L^-1, written out as the three [ld, ld] (zero padded)
+// right-hand matrices of the change of variables  y~ = L^-1 y,  x~ = L^T x  under which the row systems become
+// (I + (w-1) sum y~ y~^T) x~ = w sum y~ :   By = L^-T (Y~ = Y By),   Bfwd = L (X~ = X Bfwd),   Bbwd = L^-1 (X = X~ Bbwd).
+template <typename T>
+__global__ void __launch_bounds__(1024) chol_transforms_kernel(const double *__restrict__ A, int K, int ld, double add_diag,
+                                                               T *__restrict__ By, T *__restrict__ Bfwd, T *__restrict__ Bbwd,
+                                                               int *__restrict__ info) {
+    extern __shared__ double sm[];
+    double *L = sm;                                                // [K][K]; L^-1 columns live in per-thread arrays
+    for (int t = threadIdx.x; t < K * K; t += blockDim.x) L[t] = A[t] + ((t / K == t % K) ? add_diag : 0.0);
+    for (int t = threadIdx.x; t < ld * ld; t += blockDim.x) { By[t] = T(0); Bfwd[t] = T(0); Bbwd[t] = T(0); }
+    __syncthreads();
+    for (int k = 0; k < K; ++k) {                                  // right-looking Cholesky, lower triangle
+        const double d = L[k * K + k];
+        if (!(d > 0.0)) { if (threadIdx.x == 0 && info) *info = k + 1; }
+        __syncthreads();
+        const double s = sqrt(d > 0.0 ? d : 1.0);
+        for (int i = k + threadIdx.x; i < K; i += blockDim.x) L[i * K + k] = (i == k) ? s : L[i * K + k] / s;
+        __syncthreads();
+        const int m = K - k - 1;
+        for (int t = threadIdx.x; t < m * m; t += blockDim.x) {
+            const int i = k + 1 + t / m, j = k + 1 + t % m;
+            if (j <= i) L[i * K + j] -= L[i * K + k] * L[j * K + k];
+        }
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < K * K; t += blockDim.x) {
+        const int i = t / K, j = t - i * K;
+        if (i >= j) Bfwd[i * ld + j] = (T)L[t];                    // L     (lower triangular)
+    }
+    if (threadIdx.x < K) {                                         // column c of L^-1 by forward substitution
+        const int c = threadIdx.x;
+        double col[128];
+        for (int i = c; i < K; ++i) {
+            double acc = (i == c) ? 1.0 : 0.0;
+            for (int j = c; j < i; ++j) acc -= L[i * K + j] * col[j];
+            col[i] = acc / L[i * K + i];
+            Bbwd[i * ld + c] = (T)col[i];                          // L^-1  (lower triangular)
+            By[c * ld + i] = (T)col[i];                            // L^-T  (upper triangular): By[k][c'] = Linv[c'][k]
+        }
+    }
+}
+
+// out[r, :] = in[r, :] * B   (B is [ld, ld] in shared memory; 64-row tiles; in place allowed)
+template <typename T>
+__global__ void __launch_bounds__(256) rows_times_matrix_kernel(const T *__restrict__ in, T *__restrict__ out,
+                                                                const T *__restrict__ B, int64_t rows, int ld) {
+    extern __shared__ __align__(16) unsigned char smem_raw2[];
+    T *Bs = reinterpret_cast<T *>(smem_raw2);          // [ld][ld]
+    T *tile = Bs + ld * ld;                            // [64][ld + 1]
+    const int ts = ld + 1;
+    for (int t = threadIdx.x; t < ld * ld; t += 256) Bs[t] = B[t];
+    const int cgroups = ld / 4;                        // thread -> 4 consecutive output columns, several rows
+    const int cq = (threadIdx.x % cgroups) * 4, rsub = threadIdx.x / cgroups, rstep = 256 / cgroups;
+    for (int64_t base = (int64_t)blockIdx.x * 64; base < rows; base += (int64_t)gridDim.x * 64) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < 64 * ld; t += 256) {
+            const int rr = t / ld, c = t - rr * ld;
+            tile[rr * ts + c] = base + rr < rows ? in[(size_t)(base + rr) * ld + c] : T(0);
+        }
+        __syncthreads();
+        if (threadIdx.x < cgroups * rstep)
+            for (int r0 = rsub; r0 < 64; r0 += 4 * rstep) {        // 4 rows x 4 columns per thread and pass
+                T acc[4][4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[q][e] = T(0);
+                const T *x = tile + r0 * ts;
+#pragma unroll 2
+                for (int k = 0; k < ld; ++k) {
+                    const T *b = Bs + k * ld + cq;
+                    const T b0 = b[0], b1 = b[1], b2 = b[2], b3 = b[3];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int rr = r0 + q * rstep;
+                        const T xv = rr < 64 ? x[q * rstep * ts + k] : T(0);
+                        acc[q][0] += xv * b0; acc[q][1] += xv * b1; acc[q][2] += xv * b2; acc[q][3] += xv * b3;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int rr = r0 + q * rstep;
+                    if (rr < 64 && base + rr < rows) {
+                        T *o = out + (size_t)(base + rr) * ld + cq;
+                        o[0] = acc[q][0]; o[1] = acc[q][1]; o[2] = acc[q][2]; o[3] = acc[q][3];
+                    }
+                }
+            }
+    }
+}
+
+extern "C" int cymf_chol_transforms_dev(const double *A, int32_t K, int32_t ld, double add_diag, int dtype,
+                                        void *By, void *Bfwd, void *Bbwd, int32_t *info, void *stream) {
+    CYMF_REQUIRE(A && By && Bfwd && Bbwd && K > 0 && K <= 128 && ld >= K && ld <= 128, "bad argument");
+    const size_t smem = sizeof(double) * (size_t)K * K;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CYMF_F32) {
+        if (smem > 48 * 1024)
+            CYMF_CUDA(cudaFuncSetAttribute(chol_transforms_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        chol_transforms_kernel<float><<<1, 1024, smem, st>>>(A, K, ld, add_diag, (float *)By, (float *)Bfwd, (float *)Bbwd, info);
+    } else {
+        if (smem > 48 * 1024)
+            CYMF_CUDA(cudaFuncSetAttribute(chol_transforms_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        chol_transforms_kernel<double><<<1, 1024, smem, st>>>(A, K, ld, add_diag, (double *)By, (double *)Bfwd, (double *)Bbwd, info);
+    }
+    CYMF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int cymf_rows_times_matrix_dev(const void *in, void *out, const void *B, int dtype, int64_t rows, int32_t ld,
+                                          void *stream) {
+    CYMF_REQUIRE(in && out && B && rows >= 0 && ld > 0 && ld % 4 == 0 && ld <= 128, "bad argument");
+    if (rows == 0) return 0;
+    const size_t es = dtype == CYMF_F32 ? 4 : 8;
+    const size_t smem = es * ((size_t)ld * ld + (size_t)64 * (ld + 1));
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t blocks = (rows + 63) / 64;
+    const int64_t cap = (int64_t)sm_count() * 2;
+    if (blocks > cap) blocks = cap;
+    if (dtype == CYMF_F32) {
+        if (smem > 48 * 1024)
+            CYMF_CUDA(cudaFuncSetAttribute(rows_times_matrix_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rows_times_matrix_kernel<float><<<(unsigned)blocks, 256, smem, st>>>((const float *)in, (float *)out, (const float *)B, rows, ld);
+    } else {
+        if (smem > 48 * 1024)
+            CYMF_CUDA(cudaFuncSetAttribute(rows_times_matrix_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rows_times_matrix_kernel<double><<<(unsigned)blocks, 256, smem, st>>>((const double *)in, (double *)out, (const double *)B, rows, ld);
+    }
+    CYMF_LAUNCHED();
+    return 0;
+}
+
 extern "C" int cymf_spd_inverse_dev(const double *A, int32_t K, int32_t ld, double add_diag, int dtype,
                                     void *out_native, void *stream) {
     CYMF_REQUIRE(A && out_native && K > 0 && K <= 128 && ld >= K && ld <= 128, "bad argument");
@@ -574,7 +713,8 @@ extern "C" int cymf_als_cg_dev(const int64_t *indptr, const int32_t *indices, co
                                void *X, const void *Y, const void *G, const void *Ginv, int dtype, int32_t K, int32_t ld,
                                double weight, double cg_tol, int32_t cg_max_iter, int32_t warps_per_row,
                                int32_t stage_rows, int32_t *queue, unsigned long long *stats, void *stream) {
-    CYMF_REQUIRE(indptr && indices && order && X && Y && G && queue, "null pointer");
+    CYMF_REQUIRE(indptr && indices && order && X && Y && queue, "null pointer");
+    CYMF_REQUIRE(G || !Ginv, "Ginv without G");
     CYMF_REQUIRE(K > 0 && K <= 128 && ld >= K && ld % 4 == 0 && ld <= 128,
                  "bad shape (WMF supports num_components <= 128, ld a multiple of 4)");
     CYMF_REQUIRE(cg_tol > 0 && cg_max_iter > 0, "bad CG parameters");
@@ -663,9 +803,15 @@ extern "C" int cymf_als_half_host(const int32_t *indptr, const int32_t *indices,
     CYMF_CUDA(cudaMemcpyAsync(d_order, order.data(), (size_t)rows * 4, cudaMemcpyHostToDevice, st));
     CYMF_CUDA(cudaMemsetAsync(d_stats, 0, 16, st));
     CYMF_TRY(cymf_gram_dev(dY, dtype, n, K, ld, weight_decay, 1, ws, wsn, g64, dG, st));
-    void *dGinv = nullptr;                                       // G^-1 preconditioner: ~40 % fewer CG iterations
-    CYMF_TRY(mem.get((char **)&dGinv, (size_t)ld * ld * es));
-    CYMF_TRY(cymf_spd_inverse_dev(g64, K, ld, 0.0, dtype, dGinv, st));
+    // change of variables y~ = L^-1 y, x~ = L^T x (G = L L^T): the CG iteration then has no dense K x K product
+    void *dBy, *dBf, *dBb, *dYt;
+    CYMF_TRY(mem.get((char **)&dBy, (size_t)ld * ld * es));
+    CYMF_TRY(mem.get((char **)&dBf, (size_t)ld * ld * es));
+    CYMF_TRY(mem.get((char **)&dBb, (size_t)ld * ld * es));
+    CYMF_TRY(mem.get((char **)&dYt, (size_t)n * ld * es));
+    CYMF_TRY(cymf_chol_transforms_dev(g64, K, ld, 0.0, dtype, dBy, dBf, dBb, nullptr, st));
+    CYMF_TRY(cymf_rows_times_matrix_dev(dY, dYt, dBy, dtype, n, ld, st));
+    CYMF_TRY(cymf_rows_times_matrix_dev(dX, dX, dBf, dtype, rows, ld, st));
     {   // heaviest rows with 16 warps per row, medium with 8, the rest with 4
         std::vector<int64_t> len((size_t)rows);
         for (int64_t t = 0; t < rows; ++t) len[(size_t)t] = indptr[order[(size_t)t] + 1] - indptr[order[(size_t)t]];
@@ -674,8 +820,9 @@ extern "C" int cymf_als_half_host(const int32_t *indptr, const int32_t *indices,
         const int64_t start[3] = {0, n16, n16 + n8}, count[3] = {n16, n8, rows - n16 - n8};
         const int32_t width[3] = {16, 8, 4};
         for (int c = 0; c < 3; ++c)
-            CYMF_TRY(cymf_als_cg_dev(d_ip, d_ix, d_order + start[c], (int32_t)count[c], dX, dY, dG, dGinv, dtype, K, ld,
-                                     weight, cg_tol, cg_max_iter, width[c], 0, d_queue, d_stats, st));
+            CYMF_TRY(cymf_als_cg_dev(d_ip, d_ix, d_order + start[c], (int32_t)count[c], dX, dYt, nullptr, nullptr, dtype, K,
+                                     ld, weight, cg_tol, cg_max_iter, width[c], 0, d_queue, d_stats, st));
+        CYMF_TRY(cymf_rows_times_matrix_dev(dX, dX, dBb, dtype, rows, ld, st));
     }
     CYMF_TRY(cymf_unpack_rows_dev(dX, stage, dtype, rows, K, ld, st));
     CYMF_CUDA(cudaMemcpyAsync(X, stage, (size_t)rows * K * 8, cudaMemcpyDeviceToHost, st));

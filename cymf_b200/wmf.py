@@ -171,10 +171,12 @@ class AlsSession(object):
     replicas of W and H in dealt order); `epoch()` = user half sweep + item half sweep (wmf.pyx:111-112)."""
 
     def __init__(self, X, W, H, weight_decay, weight, *, dtype="float32", cg_tol=1e-6, cg_max_iter=128, device=None,
-                 distributed="auto", stage_rows=0, force_width=0, precondition=True):
+                 distributed="auto", stage_rows=0, force_width=0, solver="transformed"):
         torch = _lib.require_cuda()
         self.force_width = int(force_width)
-        self.precondition = bool(precondition)
+        if solver not in ("transformed", "pcg", "cg"):
+            raise ValueError("solver must be 'transformed', 'pcg' or 'cg'")
+        self.solver = solver
         import torch.distributed as dist
         self._L = _lib.lib()
         self.dist = dist if (distributed in ("auto", True) and dist.is_available() and dist.is_initialized()
@@ -218,6 +220,8 @@ class AlsSession(object):
             self.g64 = torch.empty(K * K, dtype=torch.float64, device=dev)
             self.G = torch.empty(ld * ld, dtype=tdt, device=dev)       # [ld, ld], zero padded
             self.Ginv = torch.empty(ld * ld, dtype=tdt, device=dev)
+            self.By, self.Bfwd, self.Bbwd = (torch.empty(ld * ld, dtype=tdt, device=dev) for _ in range(3))
+            self.Yt = torch.empty((max(Up, Ip), ld), dtype=tdt, device=dev)     # fixed side in transformed coordinates
             self.queue = torch.zeros(1, dtype=torch.int32, device=dev)
             self.d_stats = torch.zeros(2, dtype=torch.int64, device=dev)
         self.epochs_done = 0
@@ -260,21 +264,35 @@ class AlsSession(object):
             _lib.check(L.cymf_gram_dev(_lib.ptr(Y_full), self.dtype, Y_full.shape[0], K, ld, self.wd, 1,
                                        _lib.ptr(self.ws), self.ws.numel(), _lib.ptr(self.g64), _lib.ptr(self.G), stream))
             add_diag = 0.0
-        ginv = None
-        if self.precondition:                                    # G^-1 as CG preconditioner (f64 Gauss-Jordan, one CTA)
+        x_blk = X_full[self.rank * R:(self.rank + 1) * R]
+        g, ginv, y_used = self.G, None, Y_full
+        if self.solver == "transformed":
+            # G = L L^T; in the coordinates y~ = L^-1 y, x~ = L^T x the row systems are (I + (w-1) sum y~ y~^T) x~ =
+            # w sum y~, so the CG iteration carries no dense K x K product (three skinny GEMMs per half sweep instead)
+            _lib.check(L.cymf_chol_transforms_dev(_lib.ptr(self.g64), K, ld, add_diag, self.dtype, _lib.ptr(self.By),
+                                                  _lib.ptr(self.Bfwd), _lib.ptr(self.Bbwd), None, stream))
+            yt = self.Yt[:Y_full.shape[0]]
+            _lib.check(L.cymf_rows_times_matrix_dev(_lib.ptr(Y_full), _lib.ptr(yt), _lib.ptr(self.By), self.dtype,
+                                                    Y_full.shape[0], ld, stream))
+            _lib.check(L.cymf_rows_times_matrix_dev(_lib.ptr(x_blk), _lib.ptr(x_blk), _lib.ptr(self.Bfwd), self.dtype,
+                                                    R, ld, stream))                       # warm start in the new coordinates
+            g, y_used = None, yt
+        elif self.solver == "pcg":                               # G^-1 as CG preconditioner (f64 Gauss-Jordan, one CTA)
             _lib.check(L.cymf_spd_inverse_dev(_lib.ptr(self.g64), K, ld, add_diag, self.dtype, _lib.ptr(self.Ginv), stream))
             ginv = self.Ginv
-        x_blk = X_full[self.rank * R:(self.rank + 1) * R]
         # rows of the block are sorted heaviest first: 16 warps per row for the longest, then 8, then 4
         start = 0
         for width, count in zip((16, 8, 4), classes):
             if count:
                 _lib.check(L.cymf_als_cg_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order[start:]), count,
-                                             _lib.ptr(x_blk), _lib.ptr(Y_full), _lib.ptr(self.G), _lib.ptr(ginv),
+                                             _lib.ptr(x_blk), _lib.ptr(y_used), _lib.ptr(g), _lib.ptr(ginv),
                                              self.dtype, K, ld,
                                              self.weight, self.cg_tol, self.cg_max_iter, width, self.stage_rows,
                                              _lib.ptr(self.queue), _lib.ptr(self.d_stats), stream))
             start += count
+        if self.solver == "transformed":
+            _lib.check(L.cymf_rows_times_matrix_dev(_lib.ptr(x_blk), _lib.ptr(x_blk), _lib.ptr(self.Bbwd), self.dtype,
+                                                    R, ld, stream))                       # back to the original coordinates
         if self.dist:
             self.dist.all_gather_into_tensor(X_full, x_blk)
 

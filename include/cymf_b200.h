@@ -173,6 +173,19 @@ int cymf_als_cg_dev(const int64_t *indptr, const int32_t *indices, const int32_t
 int cymf_spd_inverse_dev(const double *A, int32_t K, int32_t ld, double add_diag, int dtype, void *out_native,
                          void *stream);
 
+/* G of cymf_als_cg_dev may be NULL: then the factors are taken to be in the coordinates y~ = L^-1 y,
+ * x~ = L^T x (G = L L^T), where every row system reads (I + (w-1) sum y~ y~^T) x~ = w sum y~ and the CG
+ * iteration has no dense K x K product at all (same Krylov space as G^-1-preconditioned CG).
+ * cymf_chol_transforms_dev factorises the dense f64 K x K matrix A (+ add_diag on the diagonal) in f64 on the
+ * device and writes the three [ld, ld] zero-padded matrices of `dtype` for cymf_rows_times_matrix_dev:
+ *     Y~ = Y * By (By = L^-T),   X~ = X * Bfwd (Bfwd = L),   X = X~ * Bbwd (Bbwd = L^-1).
+ * info (device int32, may be NULL) is set to k+1 if pivot k is not positive.
+ * cymf_rows_times_matrix_dev: out[r,:] = in[r,:] * B for [rows, ld] matrices (in place allowed). */
+int cymf_chol_transforms_dev(const double *A, int32_t K, int32_t ld, double add_diag, int dtype,
+                             void *By, void *Bfwd, void *Bbwd, int32_t *info, void *stream);
+int cymf_rows_times_matrix_dev(const void *in, void *out, const void *B, int dtype, int64_t rows, int32_t ld,
+                               void *stream);
+
 /* warps_per_row of cymf_als_cg_dev is 4, 8 or 16 (CTA width per row; each warp brings 8 KB of shared-memory
  * staging for the row's item vectors).  Given the row lengths in `order` (decreasing), this returns how many
  * leading rows should be solved with 16 warps and how many following ones with 8; the rest take 4. */
