@@ -294,7 +294,45 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
             _Pragma("unroll") for (int e = 0; e < VW; ++e)                                         \
                 acc[e] += (d0 * y0[e] + d1 * y1[e]) + (d2 * y2[e] + d3 * y3[e]);                   \
         }                                                                                          \
-        for (; i < nnz; i += 4 * NW) {                          /* mixed / streamed / tail items */ \
+        if (i < ns) { CYMF_MIXED_GROUP(); i += 4 * NW; }        /* the group that straddles the staging limit */ \
+        if (i + 3 * NW < nnz) {                                 /* streamed groups, next group's gathers in flight */ \
+            T n0[VW], n1[VW], n2[VW], n3[VW];                                                      \
+            _Pragma("unroll") for (int e = 0; e < VW; ++e) { n0[e] = n1[e] = n2[e] = n3[e] = T(0); } \
+            if (lane_on) {                                                                         \
+                ldg_vec<VW>(Yq + (size_t)__ldg(idx + i) * ld, n0);                                 \
+                ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + NW) * ld, n1);                            \
+                ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + 2 * NW) * ld, n2);                        \
+                ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + 3 * NW) * ld, n3);                        \
+            }                                                                                      \
+            for (;;) {                                                                             \
+                T y0[VW], y1[VW], y2[VW], y3[VW];                                                  \
+                _Pragma("unroll") for (int e = 0; e < VW; ++e) { y0[e] = n0[e]; y1[e] = n1[e]; y2[e] = n2[e]; y3[e] = n3[e]; } \
+                i += 4 * NW;                                                                       \
+                const bool more = i + 3 * NW < nnz;                                                \
+                if (more && lane_on) {                                                             \
+                    ldg_vec<VW>(Yq + (size_t)__ldg(idx + i) * ld, n0);                             \
+                    ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + NW) * ld, n1);                        \
+                    ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + 2 * NW) * ld, n2);                    \
+                    ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + 3 * NW) * ld, n3);                    \
+                }                                                                                  \
+                T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);                                      \
+                _Pragma("unroll") for (int e = 0; e < VW; ++e) {                                   \
+                    d0 += y0[e] * ps[e]; d1 += y1[e] * ps[e]; d2 += y2[e] * ps[e]; d3 += y3[e] * ps[e]; \
+                }                                                                                  \
+                warp_allsum4(d0, d1, d2, d3, lane);                                                \
+                _Pragma("unroll") for (int e = 0; e < VW; ++e)                                     \
+                    acc[e] += (d0 * y0[e] + d1 * y1[e]) + (d2 * y2[e] + d3 * y3[e]);               \
+                if (!more) break;                                                                  \
+            }                                                                                      \
+        }                                                                                          \
+        for (; i < nnz; i += 4 * NW) { CYMF_MIXED_GROUP(); }    /* tail */                         \
+        _Pragma("unroll") for (int e = 0; e < VW; ++e) acc[e] *= wm1;                              \
+        CYMF_APPLY_TAIL(out)                                                                       \
+    }
+
+// one group of four items that may be staged, streamed or past the end of the row
+#define CYMF_MIXED_GROUP()                                                                         \
+        {                                                                                          \
             T y0[VW], y1[VW], y2[VW], y3[VW];                                                      \
             _Pragma("unroll") for (int e = 0; e < VW; ++e) { y0[e] = y1[e] = y2[e] = y3[e] = T(0); } \
             if (lane_on) {                                                                         \
@@ -315,8 +353,10 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
             warp_allsum4(d0, d1, d2, d3, lane);                                                    \
             _Pragma("unroll") for (int e = 0; e < VW; ++e)                                         \
                 acc[e] += (d0 * y0[e] + d1 * y1[e]) + (d2 * y2[e] + d3 * y3[e]);                   \
-        }                                                                                          \
-        _Pragma("unroll") for (int e = 0; e < VW; ++e) acc[e] *= wm1;                              \
+        }
+
+// + rows [j0, j1) of G p (untransformed solvers), publish the warp's partial, barrier, combine
+#define CYMF_APPLY_TAIL(out)                                                                       \
         if (lane_on) {                                                                             \
             if (dense) {                                                                           \
                 const T *g = Gw;                                                                   \
@@ -335,8 +375,7 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
             _Pragma("unroll") for (int w_ = 0; w_ < NW; ++w_) o_ += part[w_ * CG_VEC + tid];       \
             if (!dense) o_ += p_s[tid];                /* transformed space: G = I */             \
         }                                                                                          \
-        out = o_;                                                                                  \
-    }
+        out = o_;
 
         // stage the row's item vectors and accumulate b = w * sum y_i (wmf.pyx:163)
         {
@@ -433,6 +472,8 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
 #undef CYMF_APPLY
 #undef CYMF_BLOCK_SUM
 #undef CYMF_BLOCK_SUM2
+#undef CYMF_MIXED_GROUP
+#undef CYMF_APPLY_TAIL
 #undef CYMF_PRECOND
     }
 }
@@ -455,8 +496,9 @@ template <typename T> static int gram_impl(const T *Y, int64_t n, int K, int ld,
 
 template <typename T, int VW, int NW> static int launch_cg(AlsArgs<T> a, int32_t stage_rows, cudaStream_t st) {
     const size_t fixed = sizeof(T) * ((size_t)(1 + NW) * CG_VEC + 4 * NW);
-    if (stage_rows <= 0) {                       // auto: 8 KB of staged item vectors per warp (32 / 64 / 128 KB per CTA)
-        stage_rows = (int32_t)((size_t)NW * 8 * 1024 / (sizeof(T) * a.ld));
+    if (stage_rows <= 0) {   // auto: 4 KB of staged item vectors per warp -- measured (tools/als_tune.py): resident warps
+                             // matter more than staging; 16/32/64 KB per CTA keeps >= 36 warps per SM
+        stage_rows = (int32_t)((size_t)NW * 4 * 1024 / (sizeof(T) * a.ld));
         if (stage_rows < 8) stage_rows = 8;
     }
     a.stage_rows = stage_rows;
@@ -739,11 +781,11 @@ extern "C" int cymf_als_cg_dev(const int64_t *indptr, const int32_t *indices, co
 extern "C" int cymf_als_row_classes(const int64_t *sorted_lengths_desc, int64_t n, int dtype, int32_t ld,
                                     int64_t *n_wide16, int64_t *n_wide8) {
     CYMF_REQUIRE(sorted_lengths_desc && n_wide16 && n_wide8 && n >= 0 && ld > 0, "bad argument");
-    // Measured on B200 (tools/als_tune.py, ml-20m shape, K=128): 4 warps per row win up to a few hundred entries
-    // (137 on average: 22 ms vs 28 ms with 8 and 45 ms with 16 warps), 16 warps win on rows averaging 673 entries
-    // (20 ms vs 22 ms / 30 ms); per-iteration barriers and the 1/NW-th share of G p set the crossover.
+    // Measured on B200 (tools/als_tune.py, ml-20m shape, K=128, transformed solver): rows averaging 130 entries
+    // take 11.4 ms with 4 warps per row, 13.5 ms with 8, 23 ms with 16; rows averaging 673 entries (heavy tail up
+    // to 31 k) take 12.4 / 8.9 / 11.4 ms.  Per-iteration barriers against per-warp work set the crossover.
     (void)dtype; (void)ld;
-    const int64_t wide8 = 384, wide16 = 1024;
+    const int64_t wide8 = 384, wide16 = 4096;
     int64_t a = 0, b = 0;
     while (a < n && sorted_lengths_desc[a] > wide16) ++a;
     b = a;
