@@ -643,9 +643,15 @@ __global__ void __launch_bounds__(1024) chol_transforms_kernel(const double *__r
     }
 }
 
-// out[r, :] = in[r, :] * B   (B is [ld, ld] in shared memory; 64-row tiles; in place allowed)
+// out[r, :] = in[r, :] * B   (B is [ld, ld] in shared memory; 64-row tiles; in place allowed).
+// The result tile is written to every destination in `outs`: with one destination this is a plain skinny GEMM;
+// with the peers' replicas of the factor matrix as destinations (NVLink peer memory) the kernel is the GEMM
+// AND the all-gather of the solved block -- each rank's rows land in all replicas straight from the epilogue.
+constexpr int MAX_DESTS = 8;
+template <typename T> struct MultiOut { T *p[MAX_DESTS]; int n; };
+
 template <typename T>
-__global__ void __launch_bounds__(256) rows_times_matrix_kernel(const T *__restrict__ in, T *__restrict__ out,
+__global__ void __launch_bounds__(256) rows_times_matrix_kernel(const T *__restrict__ in, const MultiOut<T> outs,
                                                                 const T *__restrict__ B, int64_t rows, int ld) {
     extern __shared__ __align__(16) unsigned char smem_raw2[];
     T *Bs = reinterpret_cast<T *>(smem_raw2);          // [ld][ld]
@@ -684,8 +690,8 @@ __global__ void __launch_bounds__(256) rows_times_matrix_kernel(const T *__restr
                 for (int q = 0; q < 4; ++q) {
                     const int rr = r0 + q * rstep;
                     if (rr < 64 && base + rr < rows) {
-                        T *o = out + (size_t)(base + rr) * ld + cq;
-                        o[0] = acc[q][0]; o[1] = acc[q][1]; o[2] = acc[q][2]; o[3] = acc[q][3];
+                        const size_t off = (size_t)(base + rr) * ld + cq;
+                        for (int d = 0; d < outs.n; ++d) st_vec<4>(outs.p[d] + off, acc[q]);
                     }
                 }
             }
@@ -710,9 +716,20 @@ extern "C" int cymf_chol_transforms_dev(const double *A, int32_t K, int32_t ld, 
     return 0;
 }
 
+extern "C" int cymf_rows_times_matrix_multi_dev(const void *in, void *const *outs, int32_t n_outs, const void *B,
+                                                int dtype, int64_t rows, int32_t ld, void *stream);
+
 extern "C" int cymf_rows_times_matrix_dev(const void *in, void *out, const void *B, int dtype, int64_t rows, int32_t ld,
                                           void *stream) {
-    CYMF_REQUIRE(in && out && B && rows >= 0 && ld > 0 && ld % 4 == 0 && ld <= 128, "bad argument");
+    void *outs[1] = {out};
+    return cymf_rows_times_matrix_multi_dev(in, outs, 1, B, dtype, rows, ld, stream);
+}
+
+extern "C" int cymf_rows_times_matrix_multi_dev(const void *in, void *const *outs, int32_t n_outs, const void *B,
+                                                int dtype, int64_t rows, int32_t ld, void *stream) {
+    CYMF_REQUIRE(in && outs && B && rows >= 0 && ld > 0 && ld % 4 == 0 && ld <= 128, "bad argument");
+    CYMF_REQUIRE(n_outs >= 1 && n_outs <= MAX_DESTS, "1..8 destinations");
+    for (int d = 0; d < n_outs; ++d) CYMF_REQUIRE(outs[d] != nullptr, "null destination");
     if (rows == 0) return 0;
     const size_t es = dtype == CYMF_F32 ? 4 : 8;
     const size_t smem = es * ((size_t)ld * ld + (size_t)64 * (ld + 1));
@@ -723,11 +740,17 @@ extern "C" int cymf_rows_times_matrix_dev(const void *in, void *out, const void 
     if (dtype == CYMF_F32) {
         if (smem > 48 * 1024)
             CYMF_CUDA(cudaFuncSetAttribute(rows_times_matrix_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rows_times_matrix_kernel<float><<<(unsigned)blocks, 256, smem, st>>>((const float *)in, (float *)out, (const float *)B, rows, ld);
+        MultiOut<float> mo{};
+        mo.n = n_outs;
+        for (int d = 0; d < n_outs; ++d) mo.p[d] = (float *)outs[d];
+        rows_times_matrix_kernel<float><<<(unsigned)blocks, 256, smem, st>>>((const float *)in, mo, (const float *)B, rows, ld);
     } else {
         if (smem > 48 * 1024)
             CYMF_CUDA(cudaFuncSetAttribute(rows_times_matrix_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rows_times_matrix_kernel<double><<<(unsigned)blocks, 256, smem, st>>>((const double *)in, (double *)out, (const double *)B, rows, ld);
+        MultiOut<double> mo{};
+        mo.n = n_outs;
+        for (int d = 0; d < n_outs; ++d) mo.p[d] = (double *)outs[d];
+        rows_times_matrix_kernel<double><<<(unsigned)blocks, 256, smem, st>>>((const double *)in, mo, (const double *)B, rows, ld);
     }
     CYMF_LAUNCHED();
     return 0;

@@ -37,7 +37,7 @@ class WMF(object):
     """
 
     def __init__(self, num_components=20, weight_decay=0.01, weight=10.0, *, dtype="float32", cg_tol=None,
-                 cg_max_iter=None, device=None, distributed="auto"):
+                 cg_max_iter=None, device=None, distributed="auto", peer_gather=True, solver="transformed"):
         self.num_components = int(num_components)
         self.weight_decay = float(weight_decay)
         self.weight = float(weight)
@@ -52,6 +52,8 @@ class WMF(object):
         self.cg_max_iter = cg_max_iter
         self.device = device
         self.distributed = distributed
+        self.peer_gather = peer_gather
+        self.solver = solver
         self.cg_iterations_ = 0          # CG iterations summed over rows, last fit
         self.cg_unconverged_ = 0         # rows that stopped at cg_max_iter, last fit
 
@@ -99,7 +101,10 @@ class WMF(object):
         W, H = self.W, self.H
         tol, iters = self._tolerances()
         sess = AlsSession(X, W, H, self.weight_decay, self.weight, dtype=self.dtype, cg_tol=tol, cg_max_iter=iters,
-                          device=self.device, distributed=self.distributed)
+                          device=self.device, distributed=self.distributed, peer_gather=self.peer_gather,
+                          solver=self.solver)
+        # how solved blocks reach the other ranks: "single" | "peer-store" (fused into the GEMM epilogue) | "nccl"
+        self.gather_mode_ = "peer-store" if sess.peer else ("nccl" if sess.dist else "single")
         W_best, H_best = (W.copy(), H.copy()) if valid_evaluator else (None, None)
         count = 0
         with tqdm(total=num_epochs, leave=True, ncols=100, disable=not verbose) as progress:
@@ -171,8 +176,9 @@ class AlsSession(object):
     replicas of W and H in dealt order); `epoch()` = user half sweep + item half sweep (wmf.pyx:111-112)."""
 
     def __init__(self, X, W, H, weight_decay, weight, *, dtype="float32", cg_tol=1e-6, cg_max_iter=128, device=None,
-                 distributed="auto", stage_rows=0, force_width=0, solver="transformed"):
+                 distributed="auto", stage_rows=0, force_width=0, solver="transformed", peer_gather=True):
         torch = _lib.require_cuda()
+        self.peer_error = None
         self.force_width = int(force_width)
         if solver not in ("transformed", "pcg", "cg"):
             raise ValueError("solver must be 'transformed', 'pcg' or 'cg'")
@@ -215,6 +221,12 @@ class AlsSession(object):
             self.order_i = torch.arange(self.Ri, dtype=torch.int32, device=dev)
             self.dW = self._upload(W, self.slot_u)
             self.dH = self._upload(H, self.slot_i)
+            # Multi-GPU: put both replicas in NVLink-mapped symmetric memory so that the back-transform GEMM can
+            # write each solved row into every rank's replica (GEMM + all-gather in one kernel).  If symmetric
+            # memory cannot be set up the blocks are exchanged with NCCL all_gather_into_tensor instead.
+            self.peer = None
+            if self.dist and peer_gather and self.solver == "transformed":
+                self.peer = self._make_symmetric()
             nws = int(self._L.cymf_gram_workspace_doubles(max(Up, Ip), K))
             self.ws = torch.empty(max(nws, 1), dtype=torch.float64, device=dev)
             self.g64 = torch.empty(K * K, dtype=torch.float64, device=dev)
@@ -227,6 +239,36 @@ class AlsSession(object):
         self.epochs_done = 0
         self.h2d_bytes = W.nbytes + H.nbytes + 8 * (self.Ru + self.Ri + 2) + 4 * (blk_u.nnz + blk_i.nnz)
         self.d2h_bytes = W.nbytes + H.nbytes
+
+    def _make_symmetric(self):
+        """Move dW / dH into symmetric memory; returns {id(tensor): (handle, [peer base pointers])} or None."""
+        import torch
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.dist.group.WORLD
+            out = {}
+            moved = []
+            for name in ("dW", "dH"):
+                old = getattr(self, name)
+                new = symm.empty(tuple(old.shape), dtype=old.dtype, device=self.dev)
+                new.copy_(old)
+                hdl = symm.rendezvous(new, group.group_name if hasattr(group, "group_name") else group)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                if len(ptrs) != self.world or ptrs[self.rank] != new.data_ptr():
+                    raise RuntimeError("unexpected symmetric-memory layout")
+                moved.append((name, new, hdl, ptrs))
+            ok = torch.ones(1, device=self.dev)
+        except Exception as exc:                                   # noqa: BLE001 - any failure -> NCCL path
+            self.peer_error = repr(exc)
+            ok = torch.zeros(1, device=self.dev)
+            moved = []
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)        # all ranks take the same path
+        if ok.item() < 1:
+            return None
+        for name, new, hdl, ptrs in moved:
+            setattr(self, name, new)
+            out[new.data_ptr()] = (hdl, ptrs)
+        return out
 
     def _upload(self, host, slots):
         """Dense f64 [rows, K] -> device [len(slots), ld] in dealt order (phantom rows zero)."""
@@ -290,6 +332,15 @@ class AlsSession(object):
                                              self.weight, self.cg_tol, self.cg_max_iter, width, self.stage_rows,
                                              _lib.ptr(self.queue), _lib.ptr(self.d_stats), stream))
             start += count
+        if self.solver == "transformed" and self.peer is not None:
+            # back-transform + all-gather in one kernel: every solved row is stored into all replicas over NVLink
+            hdl, ptrs = self.peer[X_full.data_ptr()]
+            off = self.rank * R * ld * es
+            outs = (C.c_void_p * self.world)(*[p + off for p in ptrs])
+            _lib.check(L.cymf_rows_times_matrix_multi_dev(_lib.ptr(x_blk), outs, self.world, _lib.ptr(self.Bbwd),
+                                                          self.dtype, R, ld, stream))
+            hdl.barrier(channel=0)                               # all blocks have landed in this rank's replica
+            return
         if self.solver == "transformed":
             _lib.check(L.cymf_rows_times_matrix_dev(_lib.ptr(x_blk), _lib.ptr(x_blk), _lib.ptr(self.Bbwd), self.dtype,
                                                     R, ld, stream))                       # back to the original coordinates

@@ -185,6 +185,13 @@ int cymf_chol_transforms_dev(const double *A, int32_t K, int32_t ld, double add_
                              void *By, void *Bfwd, void *Bbwd, int32_t *info, void *stream);
 int cymf_rows_times_matrix_dev(const void *in, void *out, const void *B, int dtype, int64_t rows, int32_t ld,
                                void *stream);
+/* Same product, result written to n_outs (1..8) destinations (host array of device pointers).  Multi-GPU WMF
+ * passes the address of this rank's row block inside EVERY rank's replica of the factor matrix (NVLink peer
+ * memory, e.g. torch symmetric memory): the back-transform X = X~ L^-1 and the all-gather of the solved block
+ * (cymf/wmf.pyx has no counterpart) are then one kernel -- rows reach all replicas from the
+ * GEMM epilogue.  The caller must run a cross-rank barrier before any rank reads the gathered matrix. */
+int cymf_rows_times_matrix_multi_dev(const void *in, void *const *outs, int32_t n_outs, const void *B, int dtype,
+                                     int64_t rows, int32_t ld, void *stream);
 
 /* warps_per_row of cymf_als_cg_dev is 4, 8 or 16 (CTA width per row; each warp brings 8 KB of shared-memory
  * staging for the row's item vectors).  Given the row lengths in `order` (decreasing), this returns how many

@@ -88,12 +88,16 @@ def nccl_main():
         s.fit(train, 2, 1, verbose=False)                      # every rank alone
         ew = np.abs(m.W - s.W).max() / np.abs(s.W).max()
         eh = np.abs(m.H - s.H).max() / np.abs(s.H).max()
-        print(f"rank {rank} {dtype}: sharded vs single-GPU rel err W {ew:.2e} H {eh:.2e}", flush=True)
+        print(f"rank {rank} {dtype}: sharded ({m.gather_mode_}) vs single-GPU rel err W {ew:.2e} H {eh:.2e}", flush=True)
         assert ew <= tol and eh <= tol
         t = torch.from_numpy(m.W).cuda()
         lo, hi = t.clone(), t.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         assert torch.equal(lo, hi), "ranks disagree on W"      # replicas are bit-identical across ranks
+        n = cymf.WMF(K, 0.01, 10.0, dtype=dtype, peer_gather=False)
+        n.fit(train, 2, 1, verbose=False)                      # same sharding, blocks exchanged by NCCL all-gather
+        assert n.gather_mode_ == "nccl"
+        assert np.array_equal(n.W, m.W) and np.array_equal(n.H, m.H), "peer-store and NCCL gathers differ"
     dist.destroy_process_group()
 
 
