@@ -20,7 +20,7 @@ from scipy import sparse
 from sklearn import utils
 
 from . import _lib
-from .host import init_missing_factors
+from .host import init_missing_factors, run_epochs
 
 
 def _tqdm(total, verbose, ncols=120):
@@ -100,39 +100,16 @@ class BPR(object):
     # ------------------------------------------------------------------------------------------------------
     def _fit_bpr(self, users, positives, X, num_epochs, learning_rate, weight_decay, num_threads, verbose):
         """Device replacement of `BPR._fit_bpr` (bpr.pyx:117-190); same arguments."""
-        valid_evaluator = getattr(self, "valid_evaluator", None)
-        early_stopping = getattr(self, "early_stopping", False)
         self.W = np.ascontiguousarray(self.W, dtype=np.float64)
         self.H = np.ascontiguousarray(self.H, dtype=np.float64)
-        W, H = self.W, self.H                                    # updated in place, like the reference's views
-        sess = BprSession(W, H, users, positives, X, self.optimizer, mode=self.mode, dtype=self.dtype,
+        if not hasattr(self, "valid_dcg"):
+            self.valid_dcg = -np.inf
+        # model.W / model.H are updated in place, like the reference's typed views (bpr.pyx:127-128)
+        sess = BprSession(self.W, self.H, users, positives, X, self.optimizer, mode=self.mode, dtype=self.dtype,
                           scatter=self.scatter, seed=self.seed, max_inflight=self.max_inflight, device=self.device)
-        W_best, H_best = (W.copy(), H.copy()) if valid_evaluator else (None, None)
-        count = 0
-        with _tqdm(num_epochs, verbose) as progress:
-            for epoch in range(num_epochs):
-                sess.epoch(learning_rate, weight_decay)
-                if valid_evaluator:
-                    sess.download(W, H)
-                    valid_dcg = valid_evaluator.evaluate(W, H)["DCG@5"]
-                    if early_stopping and self.valid_dcg > valid_dcg and count > 10:
-                        break
-                    elif early_stopping and self.valid_dcg > valid_dcg:
-                        count += 1
-                    else:
-                        count = 0
-                        self.valid_dcg = valid_dcg
-                        W_best, H_best = W.copy(), H.copy()
-                progress.set_description(
-                    f"EPOCH={epoch+1:{len(str(num_epochs))}} "
-                    f"{(', DCG@5=' + str(np.round(valid_dcg, 3))) if valid_evaluator else ''}")
-                progress.update(1)
-        sess.download(W, H)
+        run_epochs(self, sess, num_epochs, lambda: sess.epoch(learning_rate, weight_decay), verbose, ncols=120)
         self.n_applied_ = sess.applied()
         self.n_attempted_ = sess.N * sess.epochs_done
-        if valid_evaluator and early_stopping:
-            self.W = W_best.copy()
-            self.H = H_best.copy()
 
 
 class BprSession(object):
@@ -211,6 +188,26 @@ class BprSession(object):
         with torch.cuda.device(self.dev):
             _lib.download_factor(self.dW, self.K, W)
             _lib.download_factor(self.dH, self.K, H)
+
+    def dense_f64(self):
+        """(W, H) as dense float64 DEVICE tensors [rows, K] -- what the on-device evaluator scores."""
+        import torch
+        out = []
+        with torch.cuda.device(self.dev):
+            for m in (self.dW, self.dH):
+                t = torch.empty((m.shape[0], self.K), dtype=torch.float64, device=self.dev)
+                _lib.check(self._L.cymf_unpack_rows_dev(_lib.ptr(m), _lib.ptr(t), self.dtype, m.shape[0], self.K,
+                                                        self.ld, _lib.stream_ptr()))
+                out.append(t)
+        return tuple(out)
+
+    def snapshot(self):
+        """Device copy of the factors (best-epoch bookkeeping of early stopping, bpr.pyx:182-183)."""
+        return self.dW.clone(), self.dH.clone()
+
+    def restore(self, snap):
+        self.dW.copy_(snap[0])
+        self.dH.copy_(snap[1])
 
     def applied(self):
         return int(self.d_applied.item())

@@ -21,7 +21,7 @@ import numpy as np
 from scipy import sparse
 
 from . import _lib
-from .host import init_missing_factors
+from .host import init_missing_factors, run_epochs
 
 
 class WMF(object):
@@ -93,43 +93,18 @@ class WMF(object):
 
     def _fit_als(self, X, num_epochs, num_threads, verbose):
         """Device replacement of `WMF._fit_als` (wmf.pyx:97-132)."""
-        from tqdm import tqdm
-        valid_evaluator = getattr(self, "valid_evaluator", None)
-        early_stopping = getattr(self, "early_stopping", False)
         self.W = np.ascontiguousarray(self.W, dtype=np.float64)
         self.H = np.ascontiguousarray(self.H, dtype=np.float64)
-        W, H = self.W, self.H
+        if not hasattr(self, "valid_dcg"):
+            self.valid_dcg = -np.inf
         tol, iters = self._tolerances()
-        sess = AlsSession(X, W, H, self.weight_decay, self.weight, dtype=self.dtype, cg_tol=tol, cg_max_iter=iters,
-                          device=self.device, distributed=self.distributed, peer_gather=self.peer_gather,
-                          solver=self.solver)
+        sess = AlsSession(X, self.W, self.H, self.weight_decay, self.weight, dtype=self.dtype, cg_tol=tol,
+                          cg_max_iter=iters, device=self.device, distributed=self.distributed,
+                          peer_gather=self.peer_gather, solver=self.solver)
         # how solved blocks reach the other ranks: "single" | "peer-store" (fused into the GEMM epilogue) | "nccl"
         self.gather_mode_ = "peer-store" if sess.peer else ("nccl" if sess.dist else "single")
-        W_best, H_best = (W.copy(), H.copy()) if valid_evaluator else (None, None)
-        count = 0
-        with tqdm(total=num_epochs, leave=True, ncols=100, disable=not verbose) as progress:
-            for epoch in range(num_epochs):
-                sess.epoch()
-                if valid_evaluator:
-                    sess.download(W, H)
-                    valid_dcg = valid_evaluator.evaluate(W, H)["DCG@5"]
-                    if early_stopping and self.valid_dcg > valid_dcg and count > 10:
-                        break
-                    elif early_stopping and self.valid_dcg > valid_dcg:
-                        count += 1
-                    else:
-                        count = 0
-                        self.valid_dcg = valid_dcg
-                        W_best, H_best = W.copy(), H.copy()
-                progress.set_description(
-                    f"EPOCH={epoch+1:{len(str(num_epochs))}} "
-                    f"{(', DCG@5=' + str(np.round(valid_dcg, 3))) if valid_evaluator else ''}")
-                progress.update(1)
-        sess.download(W, H)
+        run_epochs(self, sess, num_epochs, sess.epoch, verbose, ncols=100)
         self.cg_iterations_, self.cg_unconverged_ = sess.stats()
-        if valid_evaluator and early_stopping:
-            self.W = W_best.copy()
-            self.H = H_best.copy()
 
     def _als(self, indptr, indices, X, Y, num_threads=1):
         """`WMF._als(indptr, indices, X, Y, num_threads)` (wmf.pyx:136): solves every row of the HOST array X in
@@ -179,6 +154,7 @@ class AlsSession(object):
                  distributed="auto", stage_rows=0, force_width=0, solver="transformed", peer_gather=True):
         torch = _lib.require_cuda()
         self.peer_error = None
+        self._unperm = {}
         self.force_width = int(force_width)
         if solver not in ("transformed", "pcg", "cg"):
             raise ValueError("solver must be 'transformed', 'pcg' or 'cg'")
@@ -367,6 +343,30 @@ class AlsSession(object):
                 dealt = np.empty((slots.shape[0], self.K), np.float64)
                 _lib.download_factor(dev_m, self.K, dealt)
                 out[slots[slots >= 0]] = dealt[slots >= 0]
+
+    def dense_f64(self):
+        """(W, H) as dense float64 DEVICE tensors in the caller's row order -- what the on-device evaluator scores."""
+        import torch
+        out = []
+        with torch.cuda.device(self.dev):
+            for m, slots in ((self.dW, self.slot_u), (self.dH, self.slot_i)):
+                t = torch.empty((m.shape[0], self.K), dtype=torch.float64, device=self.dev)
+                _lib.check(self._L.cymf_unpack_rows_dev(_lib.ptr(m), _lib.ptr(t), self.dtype, m.shape[0], self.K,
+                                                        self.ld, _lib.stream_ptr()))
+                key = id(slots)
+                if key not in self._unperm:                       # position of every original row in dealt order
+                    pos = np.empty(int((slots >= 0).sum()), np.int64)
+                    pos[slots[slots >= 0]] = np.flatnonzero(slots >= 0)
+                    self._unperm[key] = torch.from_numpy(pos).to(self.dev)
+                out.append(t.index_select(0, self._unperm[key]))
+        return tuple(out)
+
+    def snapshot(self):
+        return self.dW.clone(), self.dH.clone()
+
+    def restore(self, snap):
+        self.dW.copy_(snap[0])
+        self.dH.copy_(snap[1])
 
     def stats(self):
         s = self.d_stats.cpu().numpy()

@@ -117,6 +117,39 @@ def test_hogwild_red_scatter_equals_store_when_serial(oracle):
     assert np.abs(out[0][1] - out[1][1]).max() <= 1e-13
 
 
+def test_validation_on_device_equals_host_path():
+    """fit(valid_evaluator=..., early_stopping=True): cymf_b200's evaluator scores the device-resident factors and the
+    best epoch is snapshotted on the device; any other evaluator object gets NumPy arrays as in the reference
+    (bpr.pyx:173-190).  Both paths must select the same epoch and return the same factors (replay mode is
+    deterministic)."""
+    import cymf_b200 as cymf
+    train, test = cymf.synth.movielens_like("ml-100k")
+    ev = cymf.evaluator.AverageOverAllEvaluator(test, train, k=5)
+
+    class Foreign:                                  # not an instance of cymf_b200.Evaluator -> host path
+        def __init__(self, inner):
+            self.inner, self.calls = inner, 0
+
+        def evaluate(self, W, H):
+            assert isinstance(W, np.ndarray) and isinstance(H, np.ndarray)
+            self.calls += 1
+            return self.inner.evaluate(W, H)
+
+    sub = train[:200]
+    sub_test = test[:200]
+    ev_small = cymf.evaluator.AverageOverAllEvaluator(sub_test, sub, k=5)
+    out = []
+    for evaluator in (ev_small, Foreign(ev_small)):
+        m = cymf.BPR(8, 0.05, "sgd", 0.01, mode="replay")
+        m.fit(sub, num_epochs=4, valid_evaluator=evaluator, early_stopping=True, verbose=False)
+        out.append((m.W.copy(), m.H.copy(), m.valid_dcg))
+    assert out[0][2] == out[1][2] > 0
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    h = cymf.BPR(20, 0.01, "adam", 0.01)
+    h.fit(train, num_epochs=5, valid_evaluator=ev, verbose=False)          # Hogwild + on-device validation
+    assert h.valid_dcg > 0.05 and np.isfinite(h.W).all()
+
+
 def _mean_metrics(oracle, W, H, test, train):
     rs = [oracle.evaluate(W, H, test, train, k=5, seed=s) for s in range(5)]     # optuna_example.py:63-65
     return {k: float(np.mean([r[k] for r in rs])) for k in rs[0]}
