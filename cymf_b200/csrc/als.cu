@@ -100,7 +100,12 @@ __global__ void gram_finish_kernel(const double *__restrict__ partial, int slabs
     const int i = t / ld, j = t - i * ld;
     double s = 0.0;
     if (i < K && j < K) {
-        for (int b = 0; b < slabs; ++b) s += partial[(size_t)b * K * K + i * K + j];
+        // (P + P^T) / 2: exactly symmetric whatever the order in which the partials were accumulated (the 3xTF32
+        // tensor-core path adds hi*lo and lo*hi in different MMAs, so P[i][j] and P[j][i] can differ in the last bit)
+        for (int b = 0; b < slabs; ++b) {
+            const double *p = partial + (size_t)b * K * K;
+            s += 0.5 * (p[i * K + j] + p[j * K + i]);
+        }
         if (i == j) s += wd;
         if (out64) out64[i * K + j] = s;
     }
@@ -480,6 +485,16 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
 
 template <typename T> static int gram_impl(const T *Y, int64_t n, int K, int ld, double wd, int add_wd, double *partial,
                                            int64_t partial_capacity, double *out64, T *outT, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) {
+        if (tc_enabled() && tc_shape_ok(CYMF_F32, ld)) {          // tensor cores: 3xTF32 tcgen05 partials per 256-row slab
+            const int tslabs = (int)tc_gram_slabs(n);
+            if ((int64_t)tslabs * K * K > partial_capacity) { set_error("gram: workspace too small"); return CYMF_EINVAL; }
+            CYMF_TRY(tc_gram_partial((const float *)Y, n, K, ld, partial, st));
+            gram_finish_kernel<T><<<(ld * ld + 255) / 256, 256, 0, st>>>(partial, tslabs, K, ld, add_wd ? wd : 0.0, out64, outT);
+            CYMF_LAUNCHED();
+            return 0;
+        }
+    }
     const int slabs = (int)((n + GRAM_SLAB - 1) / GRAM_SLAB);
     if ((int64_t)slabs * K * K > partial_capacity) { set_error("gram: workspace too small"); return CYMF_EINVAL; }
     if (slabs > 0) {
@@ -535,7 +550,8 @@ template <typename T> static int cg_impl(const AlsArgs<T> &a, int32_t warps_per_
 using namespace cymf;
 
 extern "C" int64_t cymf_gram_workspace_doubles(int64_t n, int32_t K) {
-    return ((n + GRAM_SLAB - 1) / GRAM_SLAB) * (int64_t)K * K;
+    const int64_t a = (n + GRAM_SLAB - 1) / GRAM_SLAB, b = tc_gram_slabs(n);     // FFMA / tcgen05 slab counts
+    return (a > b ? a : b) * (int64_t)K * K;
 }
 
 extern "C" int cymf_gram_dev(const void *Y, int dtype, int64_t n, int32_t K, int32_t ld, double weight_decay,
@@ -731,6 +747,9 @@ extern "C" int cymf_rows_times_matrix_multi_dev(const void *in, void *const *out
     CYMF_REQUIRE(n_outs >= 1 && n_outs <= MAX_DESTS, "1..8 destinations");
     for (int d = 0; d < n_outs; ++d) CYMF_REQUIRE(outs[d] != nullptr, "null destination");
     if (rows == 0) return 0;
+    if (tc_enabled() && tc_shape_ok(dtype, ld))                  // tensor cores (tcgen05, 3xTF32), tc_gemm.cu
+        return tc_rows_times_matrix((const float *)in, (float *const *)outs, n_outs, (const float *)B, rows, ld,
+                                    (cudaStream_t)stream);
     const size_t es = dtype == CYMF_F32 ? 4 : 8;
     const size_t smem = es * ((size_t)ld * ld + (size_t)64 * (ld + 1));
     cudaStream_t st = (cudaStream_t)stream;

@@ -25,6 +25,11 @@ int cuda_status(cudaError_t e, const char *what, const char *file, int line) {
     return (int)e;
 }
 
+bool tc_enabled() {
+    const char *v = getenv("CYMF_NO_TCGEN05");
+    return !(v && v[0] == '1');
+}
+
 int sm_count() {
     static int cached = 0;
     if (!cached) {

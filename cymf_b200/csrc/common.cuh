@@ -33,6 +33,14 @@ int sm_count();
         CYMF_CUDA(cudaGetLastError());                             \
     } while (0)
 
+// tcgen05 (tensor core) implementations of the GEMM-shaped pieces, tc_gemm.cu; f32, ld in {32, 64, 96, 128}
+bool tc_shape_ok(int dtype, int ld);
+int tc_rows_times_matrix(const float *in, float *const *outs, int n_outs, const float *B, int64_t rows, int ld,
+                         cudaStream_t st);
+int64_t tc_gram_slabs(int64_t n);
+int tc_gram_partial(const float *Y, int64_t n, int K, int ld, double *partial, cudaStream_t st);
+bool tc_enabled();      // false when the environment sets CYMF_NO_TCGEN05=1 (A/B comparisons in tests and tools)
+
 #define CYMF_TRY(expr)             \
     do {                           \
         int rc_ = (expr);          \

@@ -1,0 +1,319 @@
+// tc_gemm.cu -- the GEMM-shaped pieces of the WMF half sweep on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+//   tc_rows_times_matrix_kernel : out[r, :] = in[r, :] * B  for [rows, ld] f32 matrices, B [ld, ld]  (the three changes of
+//       variables of the transformed ALS solver: Y~ = Y L^-T, X~ = X L, X = X~ L^-1).  One CTA per 128-row tile,
+//       accumulator D[128 x ld] in tensor memory, operands staged in shared memory in the canonical K-major
+//       no-swizzle UMMA layout.  The epilogue reads D back with tcgen05.ld and stores every row to ALL destinations
+//       it is given -- with the peers' replicas of the factor matrix as destinations this one kernel is the GEMM and
+//       the all-gather over NVLink peer memory.
+//   tc_gram_partial_kernel      : per-slab partial of G = Y^T Y (cymf/wmf.pyx:142) with the same machinery; slabs are
+//       summed in f64 in a fixed order by gram_finish_kernel (als.cu).
+//
+// Precision: kind::tf32 keeps 10 mantissa bits per operand, far too few for the 1e-4 parity bar, so every operand
+// is split as a = hi + lo (hi = a with the low 13 mantissa bits cleared, lo = a - hi, both exactly representable) and
+// three MMAs are issued per k-slice: hi*hi + hi*lo + lo*hi ("3xTF32"); the dropped lo*lo term is ~2^-22 relative.
+// Accumulation is f32 in TMEM.
+#include "common.cuh"
+
+namespace cymf {
+namespace tc {
+
+constexpr int TILE_M = 128;       // rows of D (TMEM lanes)
+constexpr int CHUNK_K = 32;       // reduction elements staged per step: 8 x 16-byte chunks, 4 MMA k-slices of 8
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they have completed
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, M = 128, N from the instruction descriptor, K = 8
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared-memory matrix descriptor, canonical K-major layout without swizzle: 8-row x 16-byte core matrices, rows of a
+// core matrix 16 bytes apart, `sbo` bytes between 8-row groups, `lbo` bytes between the two 16-byte K chunks of a slice
+__device__ __forceinline__ uint64_t smem_desc(const void *p, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_u32(p) >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// instruction descriptor: D f32, A/B tf32, both K-major, dense, M = 128
+__host__ __device__ constexpr uint32_t idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+// 32 consecutive f32 columns of this warp's 32 TMEM lanes: thread l of the warp receives lane (row) l
+__device__ __forceinline__ void tmem_load32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int t = 0; t < 32; ++t) v[t] = __uint_as_float(r[t]);
+}
+
+__device__ __forceinline__ float4 tf32_hi(float4 a) {
+    return make_float4(__uint_as_float(__float_as_uint(a.x) & 0xffffe000u), __uint_as_float(__float_as_uint(a.y) & 0xffffe000u),
+                       __uint_as_float(__float_as_uint(a.z) & 0xffffe000u), __uint_as_float(__float_as_uint(a.w) & 0xffffe000u));
+}
+__device__ __forceinline__ float4 sub4(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+
+// Operand tile in shared memory: `groups` 8-row groups x 8 chunks of 16 bytes (32 reduction elements):
+//   byte offset of (row m, chunk q) = q * groups * 128 + (m / 8) * 128 + (m % 8) * 16
+__device__ __forceinline__ int tile_off(int m, int q, int groups) { return (q * groups * 128 + (m >> 3) * 128 + (m & 7) * 16) >> 2; }
+
+// issue the 3 x 4 MMAs of one staged 32-element reduction chunk (thread 0 only)
+__device__ __forceinline__ void issue_chunk(uint32_t d_tmem, const float *a_hi, const float *a_lo, const float *b_hi,
+                                            const float *b_lo, int a_groups, int b_groups, uint32_t idesc, bool first) {
+    const uint32_t lbo_a = a_groups * 128, lbo_b = b_groups * 128;
+#pragma unroll
+    for (int ks = 0; ks < CHUNK_K / 8; ++ks) {
+        const uint64_t ah = smem_desc(a_hi + ks * 2 * (lbo_a >> 2), lbo_a, 128), al = smem_desc(a_lo + ks * 2 * (lbo_a >> 2), lbo_a, 128);
+        const uint64_t bh = smem_desc(b_hi + ks * 2 * (lbo_b >> 2), lbo_b, 128), bl = smem_desc(b_lo + ks * 2 * (lbo_b >> 2), lbo_b, 128);
+        mma_tf32(d_tmem, ah, bl, idesc, (first && ks == 0) ? 0u : 1u);     // small terms first
+        mma_tf32(d_tmem, al, bh, idesc, 1u);
+        mma_tf32(d_tmem, ah, bh, idesc, 1u);
+    }
+}
+
+constexpr int MAX_DESTS = 8;
+struct MultiOutF { float *p[MAX_DESTS]; int n; };
+
+__global__ void __launch_bounds__(128) tc_rows_times_matrix_kernel(const float *__restrict__ in, const MultiOutF outs,
+                                                                   const float *__restrict__ B, int64_t rows, int ld,
+                                                                   uint32_t tmem_cols) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *a_hi = reinterpret_cast<float *>(smem_raw);            // [TILE_M x 32]
+    float *a_lo = a_hi + TILE_M * CHUNK_K;
+    float *b_hi = a_lo + TILE_M * CHUNK_K;                        // [ld x 32]
+    float *b_lo = b_hi + ld * CHUNK_K;
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
+    if (tid == 0) mbar_init(&mbar, 1);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t d_tmem = tmem_slot;
+    const uint32_t idesc = idesc_tf32(ld);
+    const int a_groups = TILE_M / 8, b_groups = ld / 8;
+    uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile * TILE_M < rows; tile += gridDim.x) {
+        const int64_t row0 = tile * TILE_M;
+        for (int kc = 0; kc < ld / CHUNK_K; ++kc) {
+            {   // A chunk: thread m stages row m, columns [32 kc, 32 kc + 32)
+                const bool ok = row0 + tid < rows;
+                const float4 *src = reinterpret_cast<const float4 *>(in + (size_t)(row0 + tid) * ld + kc * CHUNK_K);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 v = ok ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 h = tf32_hi(v);
+                    const int o = tile_off(tid, q, a_groups);
+                    *reinterpret_cast<float4 *>(a_hi + o) = h;
+                    *reinterpret_cast<float4 *>(a_lo + o) = sub4(v, h);
+                }
+            }
+            if (tid < ld) {   // B chunk: operand element (n, k) = B[32 kc + k][n]; thread n
+                const float *src = B + (size_t)kc * CHUNK_K * ld + tid;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 v = make_float4(__ldg(src + (4 * q) * ld), __ldg(src + (4 * q + 1) * ld),
+                                                 __ldg(src + (4 * q + 2) * ld), __ldg(src + (4 * q + 3) * ld));
+                    const float4 h = tf32_hi(v);
+                    const int o = tile_off(tid, q, b_groups);
+                    *reinterpret_cast<float4 *>(b_hi + o) = h;
+                    *reinterpret_cast<float4 *>(b_lo + o) = sub4(v, h);
+                }
+            }
+            fence_async_smem();                      // generic-proxy writes -> visible to the tensor core (async proxy)
+            __syncthreads();
+            if (tid == 0) {
+                fence_after_sync();
+                // every 32-element reduction chunk gets its own accumulator (TMEM columns [kc ld, kc ld + ld)):
+                // the tensor core truncates when it adds into D, so short chains (12 MMAs) keep the f32 result
+                // within ~6e-7 of exact; the chunk sums are added in registers in the epilogue
+                issue_chunk(d_tmem + (uint32_t)(kc * ld), a_hi, a_lo, b_hi, b_lo, a_groups, b_groups, idesc, true);
+                mma_commit(&mbar);
+            }
+            mbar_wait(&mbar, phase);                 // MMAs of this chunk are done: operands may be overwritten
+            phase ^= 1u;
+        }
+        fence_after_sync();
+        const int64_t row = row0 + warp * 32 + lane;
+        for (int c0 = 0; c0 < ld; c0 += 32) {        // epilogue: TMEM -> registers -> every destination
+            float v[32];
+            tmem_load32(d_tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            for (int kc = 1; kc < ld / CHUNK_K; ++kc) {
+                float u[32];
+                tmem_load32(d_tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(kc * ld + c0), u);
+#pragma unroll
+                for (int t = 0; t < 32; ++t) v[t] += u[t];
+            }
+            if (row < rows)
+                for (int d = 0; d < outs.n; ++d) {
+                    float4 *o = reinterpret_cast<float4 *>(outs.p[d] + (size_t)row * ld + c0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+        }
+        fence_before_sync();
+        __syncthreads();                             // D has been read: the next tile may overwrite it
+        fence_after_sync();
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(d_tmem, tmem_cols);
+}
+
+// partial[slab] = Y[slab rows]^T Y[slab rows]  (dense [K, K] doubles, like gram_partial_kernel).
+// Each 32-row chunk is multiplied on the tensor cores into a fresh TMEM accumulator (12 MMAs), read back and added
+// into an f64 copy of the slab's result in shared memory, so the truncating f32 accumulation never runs long chains.
+constexpr int TC_GRAM_SLAB = 512;
+
+__global__ void __launch_bounds__(128) tc_gram_partial_kernel(const float *__restrict__ Y, int64_t n, int K, int ld,
+                                                              double *__restrict__ partial, uint32_t tmem_cols) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *t_hi = reinterpret_cast<float *>(smem_raw);            // [TILE_M x 32]: operand rows = columns of Y (zero past ld)
+    float *t_lo = t_hi + TILE_M * CHUNK_K;
+    double *acc = reinterpret_cast<double *>(t_lo + TILE_M * CHUNK_K);   // [ld][TILE_M]: acc[c][m] = G[m][c] so far
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
+    if (tid == 0) mbar_init(&mbar, 1);
+    for (int c = 0; c < ld; ++c) acc[c * TILE_M + tid] = 0.0;
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t d_tmem = tmem_slot;
+    const uint32_t idesc = idesc_tf32(ld);
+    const int groups = TILE_M / 8;
+    const int64_t r0 = (int64_t)blockIdx.x * TC_GRAM_SLAB;
+    const int64_t r1 = r0 + TC_GRAM_SLAB < n ? r0 + TC_GRAM_SLAB : n;
+    uint32_t phase = 0;
+    for (int64_t base = r0; base < r1; base += CHUNK_K) {
+        // operand element (m, k) = Y[base + k][m]; thread m (column of Y), zero rows for m >= ld or past the slab
+        const float *src = Y + (size_t)base * ld + tid;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float e[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) e[t] = (tid < ld && base + 4 * q + t < r1) ? __ldg(src + (size_t)(4 * q + t) * ld) : 0.f;
+            const float4 v = make_float4(e[0], e[1], e[2], e[3]);
+            const float4 h = tf32_hi(v);
+            const int o = tile_off(tid, q, groups);
+            *reinterpret_cast<float4 *>(t_hi + o) = h;
+            *reinterpret_cast<float4 *>(t_lo + o) = sub4(v, h);
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+            // the B operand is the same tile restricted to its first ld rows (same base address, same strides)
+            issue_chunk(d_tmem, t_hi, t_lo, t_hi, t_lo, groups, groups, idesc, true);
+            mma_commit(&mbar);
+        }
+        mbar_wait(&mbar, phase);
+        phase ^= 1u;
+        fence_after_sync();
+        for (int c0 = 0; c0 < ld; c0 += 32) {                    // D row m = column m of Y -> this thread's f64 column
+            float v[32];
+            tmem_load32(d_tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int t = 0; t < 32; ++t) acc[(c0 + t) * TILE_M + tid] += (double)v[t];
+        }
+        fence_before_sync();
+        __syncthreads();                                          // D was read: the next chunk may overwrite it
+        fence_after_sync();
+    }
+    double *out = partial + (size_t)blockIdx.x * K * K;
+    if (tid < K)
+        for (int c = 0; c < K; ++c) out[(size_t)tid * K + c] = acc[c * TILE_M + tid];
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(d_tmem, tmem_cols);
+}
+
+// power-of-two TMEM columns for `accs` accumulators of ld columns each
+static uint32_t tmem_columns(int ld, int accs) {
+    const int need = ld * accs;
+    uint32_t c = 32;
+    while ((int)c < need) c <<= 1;
+    return c;
+}
+
+}  // namespace tc
+
+// ---- entry points used by als.cu ----------------------------------------------------------------------------------
+bool tc_shape_ok(int dtype, int ld) { return dtype == CYMF_F32 && ld % 32 == 0 && ld >= 32 && ld <= 128; }
+
+int tc_rows_times_matrix(const float *in, float *const *outs, int n_outs, const float *B, int64_t rows, int ld,
+                         cudaStream_t st) {
+    tc::MultiOutF mo{};
+    mo.n = n_outs;
+    for (int d = 0; d < n_outs; ++d) mo.p[d] = outs[d];
+    const size_t smem = sizeof(float) * (size_t)(2 * tc::TILE_M * tc::CHUNK_K + 2 * ld * tc::CHUNK_K);
+    // static (mbarrier, TMEM slot) + dynamic shared memory can exceed the 48 KB default already at ld = 64
+    CYMF_CUDA(cudaFuncSetAttribute(tc::tc_rows_times_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = (rows + tc::TILE_M - 1) / tc::TILE_M;
+    // one accumulator per reduction chunk: ld = 128 takes all 512 TMEM columns, so one CTA per SM there
+    const int64_t cap = (int64_t)sm_count() * (ld >= 96 ? 1 : 3);
+    if (blocks > cap) blocks = cap;
+    tc::tc_rows_times_matrix_kernel<<<(unsigned)blocks, 128, smem, st>>>(in, mo, B, rows, ld,
+                                                                         tc::tmem_columns(ld, ld / tc::CHUNK_K));
+    CYMF_LAUNCHED();
+    return 0;
+}
+
+int64_t tc_gram_slabs(int64_t n) { return (n + tc::TC_GRAM_SLAB - 1) / tc::TC_GRAM_SLAB; }
+
+int tc_gram_partial(const float *Y, int64_t n, int K, int ld, double *partial, cudaStream_t st) {
+    const int64_t slabs = tc_gram_slabs(n);
+    if (slabs == 0) return 0;
+    const size_t smem = sizeof(float) * (size_t)(2 * tc::TILE_M * tc::CHUNK_K) + sizeof(double) * (size_t)ld * tc::TILE_M;
+    CYMF_CUDA(cudaFuncSetAttribute(tc::tc_gram_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc::tc_gram_partial_kernel<<<(unsigned)slabs, 128, smem, st>>>(Y, n, K, ld, partial, tc::tmem_columns(ld, 1));
+    CYMF_LAUNCHED();
+    return 0;
+}
+
+}  // namespace cymf
