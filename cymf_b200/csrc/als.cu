@@ -624,37 +624,68 @@ __global__ void __launch_bounds__(1024) chol_transforms_kernel(const double *__r
                                                                T *__restrict__ By, T *__restrict__ Bfwd, T *__restrict__ Bbwd,
                                                                int *__restrict__ info) {
     extern __shared__ double sm[];
-    double *L = sm;                                                // [K][K]; L^-1 columns live in per-thread arrays
-    for (int t = threadIdx.x; t < K * K; t += blockDim.x) L[t] = A[t] + ((t / K == t % K) ? add_diag : 0.0);
-    for (int t = threadIdx.x; t < ld * ld; t += blockDim.x) { By[t] = T(0); Bfwd[t] = T(0); Bbwd[t] = T(0); }
+    const int S = K + 1;                     // padded row stride: column accesses L[j][k] spread over the banks
+    double *L = sm;                          // [K][S]
+    double *part = sm + K * S;               // [2][8][128] partial sums of the forward substitution
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    for (int t = tid; t < K * K; t += blockDim.x) {
+        const int i = t / K, j = t - i * K;
+        L[i * S + j] = A[t] + (i == j ? add_diag : 0.0);
+    }
+    for (int t = tid; t < ld * ld; t += blockDim.x) { By[t] = T(0); Bfwd[t] = T(0); Bbwd[t] = T(0); }
     __syncthreads();
-    for (int k = 0; k < K; ++k) {                                  // right-looking Cholesky, lower triangle
-        const double d = L[k * K + k];
-        if (!(d > 0.0)) { if (threadIdx.x == 0 && info) *info = k + 1; }
-        __syncthreads();
-        const double s = sqrt(d > 0.0 ? d : 1.0);
-        for (int i = k + threadIdx.x; i < K; i += blockDim.x) L[i * K + k] = (i == k) ? s : L[i * K + k] / s;
-        __syncthreads();
-        const int m = K - k - 1;
-        for (int t = threadIdx.x; t < m * m; t += blockDim.x) {
-            const int i = k + 1 + t / m, j = k + 1 + t % m;
-            if (j <= i) L[i * K + j] -= L[i * K + k] * L[j * K + k];
+    // Right-looking factorisation with the column scaling deferred (L D L^T form): step k only subtracts
+    // l_ik l_jk / d_k from the trailing block, so one barrier per step suffices; columns are divided by sqrt(d_k)
+    // in a single pass at the end.
+    for (int k = 0; k < K; ++k) {
+        const double d = L[k * S + k];
+        if (!(d > 0.0) && tid == 0 && info) *info = k + 1;
+        const double inv_d = 1.0 / (d > 0.0 ? d : 1.0);
+        for (int i = k + 1 + ty; i < K; i += 32) {                 // 32 x 32 thread tile over the trailing block
+            const double lik = L[i * S + k] * inv_d;
+            for (int j = k + 1 + tx; j <= i; j += 32) L[i * S + j] -= lik * L[j * S + k];
         }
         __syncthreads();
     }
-    for (int t = threadIdx.x; t < K * K; t += blockDim.x) {
+    for (int t = tid; t < K * K; t += blockDim.x) {
         const int i = t / K, j = t - i * K;
-        if (i >= j) Bfwd[i * ld + j] = (T)L[t];                    // L     (lower triangular)
+        if (i > j) { const double dj = L[j * S + j]; L[i * S + j] = L[i * S + j] / sqrt(dj > 0.0 ? dj : 1.0); }
     }
-    if (threadIdx.x < K) {                                         // column c of L^-1 by forward substitution
-        const int c = threadIdx.x;
-        double col[128];
-        for (int i = c; i < K; ++i) {
-            double acc = (i == c) ? 1.0 : 0.0;
-            for (int j = c; j < i; ++j) acc -= L[i * K + j] * col[j];
-            col[i] = acc / L[i * K + i];
-            Bbwd[i * ld + c] = (T)col[i];                          // L^-1  (lower triangular)
-            By[c * ld + i] = (T)col[i];                            // L^-T  (upper triangular): By[k][c'] = Linv[c'][k]
+    __syncthreads();
+    for (int k = tid; k < K; k += blockDim.x) { const double dk = L[k * S + k]; L[k * S + k] = sqrt(dk > 0.0 ? dk : 1.0); }
+    __syncthreads();
+    for (int t = tid; t < K * K; t += blockDim.x) {
+        const int i = t / K, j = t - i * K;
+        if (i >= j) Bfwd[i * ld + j] = (T)L[i * S + j];            // L     (lower triangular)
+    }
+    // L^-1 by forward substitution, all K columns at once: row i of every column needs rows < i, so rows are
+    // serial; thread (c, s) accumulates the terms j = s (mod 8) of column c and owns the entries i = s (mod 8)
+    const int c = tid & 127, sgrp = tid >> 7;
+    double mine[16];                                               // Linv[8 q + sgrp][c]
+#pragma unroll
+    for (int q = 0; q < 16; ++q) mine[q] = 0.0;
+    for (int i = 0; i < K; ++i) {
+        double acc = 0.0;
+        if (c < K && c <= i) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int j = 8 * q + sgrp;
+                if (j >= c && j < i) acc += L[i * S + j] * mine[q];
+            }
+        }
+        double *pb = part + (i & 1) * 1024;
+        pb[sgrp * 128 + c] = acc;
+        __syncthreads();
+        if (sgrp == (i & 7) && c < K && c <= i) {
+            double sum = 0.0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) sum += pb[g * 128 + c];
+            const double v = ((i == c ? 1.0 : 0.0) - sum) / L[i * S + i];
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                if (q == (i >> 3)) mine[q] = v;
+            Bbwd[i * ld + c] = (T)v;                               // L^-1  (lower triangular)
+            By[c * ld + i] = (T)v;                                 // L^-T  (upper triangular): By[k][c'] = Linv[c'][k]
         }
     }
 }
@@ -717,7 +748,7 @@ __global__ void __launch_bounds__(256) rows_times_matrix_kernel(const T *__restr
 extern "C" int cymf_chol_transforms_dev(const double *A, int32_t K, int32_t ld, double add_diag, int dtype,
                                         void *By, void *Bfwd, void *Bbwd, int32_t *info, void *stream) {
     CYMF_REQUIRE(A && By && Bfwd && Bbwd && K > 0 && K <= 128 && ld >= K && ld <= 128, "bad argument");
-    const size_t smem = sizeof(double) * (size_t)K * K;
+    const size_t smem = sizeof(double) * ((size_t)K * (K + 1) + 2048);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == CYMF_F32) {
         if (smem > 48 * 1024)
