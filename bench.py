@@ -181,7 +181,8 @@ def time_als(train, K, dtype, steps, warmup, sync_all, world, hbm):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     sec = float(t[0])
     rows = (train.shape[0] + train.shape[1]) / world
-    out = {"sec_per_epoch": sec, "n_gpus": world, "nnz": int(train.nnz), "K": K, "dtype": dtype,
+    out = {"sec_per_epoch": sec, "n_gpus": world, "nnz": int(train.nnz), "K": K, "dtype": dtype, "solver": s.solver,
+           "gather": "peer-store (fused into the GEMM epilogue)" if s.peer else ("nccl all-gather" if s.dist else "single"),
            "cg_iterations_per_row": (s.stats()[0] - it0) / (steps * 2 * rows) * 2, "cg_tol": s.cg_tol,
            "unconverged_rows": s.stats()[1], "algorithmic_GBps": s.bytes_per_epoch / sec / 1e9,
            "frac_of_hbm_peak": s.bytes_per_epoch / sec / 1e9 / (hbm * world)}
@@ -394,7 +395,11 @@ def main():
                         "steps": e_steps, "call": "cymf_b200.BPR._fit_bpr(users, positives, X, 1, lr, wd, 1, False)"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                             "traffic": None, "peak_source": peak_src, "kernel": "bpr_hogwild_kernel<float,SGD,32,1,RED>",
+                             # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
+                             # command (profiles/r1_bpr_hogwild_k128_ncu_full.txt): 9.274 GB + 3.882 GB
+                             "traffic": 13.156e9, "traffic_unit": "bytes/launch",
+                             "algorithmic_bytes_per_launch": (applied / args.steps) * bpu,
+                             "peak_source": peak_src, "kernel": "bpr_hogwild_kernel<float,SGD,32,1,RED>",
                              "bytes_per_update": bpu,
                              "note": "factors (85 MB) fit the 126 MB L2, so algorithmic bytes/s may exceed DRAM bytes/s"},
                 "cpu_baseline": cpu, "extra": extra}
