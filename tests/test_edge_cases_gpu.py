@@ -1,0 +1,122 @@
+"""Edge cases of every CUDA path against the oracle (pytest -m gpu): reference defaults whose K is not a multiple
+of 4 or 32 (padding, FFMA fallbacks of the tcgen05 kernels), ragged / empty rows and columns, one-row and one-column
+matrices, users that own every item (every negative collides), duplicate co-occurrence samples."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(got, want):
+    return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-300))
+
+
+@pytest.mark.parametrize("K", [1, 3, 20, 50, 130])
+def test_bpr_replay_any_k(oracle, K):
+    """K = 20 is the reference default (bpr.pyx:50); 1, 3, 50, 130 exercise padding and multi-slot lanes."""
+    import cymf_b200 as cymf
+    X = cymf.synth.synth_implicit(40, 70, 500, seed=K)
+    m = cymf.BPR(K, 0.05, "adam", 0.01, mode="replay")
+    m.fit(X, num_epochs=2, verbose=False)
+    Xc, W, H, users, positives = oracle.bpr_prologue(X, K)
+    oracle.bpr_fit(W, H, users, positives, Xc, 2, 0.05, 0.01, "adam")
+    assert np.array_equal(m.W, W) and np.array_equal(m.H, H)
+
+
+def test_bpr_ragged_and_saturated_rows(oracle):
+    """Empty users / items, a user that owns the whole catalogue (all negatives skipped, bpr.pyx:166-167)."""
+    import cymf_b200 as cymf
+    rng = np.random.default_rng(0)
+    A = (rng.random((12, 9)) < 0.3).astype(float)
+    A[2, :] = 0          # user without positives
+    A[:, 4] = 0          # item nobody has
+    A[5, :] = 1          # user with every item: every draw collides
+    X = sparse.csr_matrix(A)
+    for mode, dtype in (("replay", "float64"), ("hogwild", "float32")):
+        m = cymf.BPR(4, 0.05, "sgd", 0.01, mode=mode, dtype=dtype, max_inflight=1)
+        m.fit(X, num_epochs=3, verbose=False)
+        Xc, W, H, users, positives = oracle.bpr_prologue(X, 4)
+        rec = oracle.bpr_fit(W, H, users, positives, Xc, 3, 0.05, 0.01, "sgd", record=True)
+        assert np.isfinite(m.W).all() and np.isfinite(m.H).all()
+        if mode == "replay":
+            assert np.array_equal(m.W, W) and np.array_equal(m.H, H)
+            assert m.n_applied_ == int(rec["applied"].sum())
+            assert np.array_equal(m.W[2], oracle.init_factors(12, 9, 4)[0][2])      # untouched row keeps its init
+    one = cymf.BPR(4, 0.05, "sgd", 0.01, mode="replay")
+    one.fit(sparse.csr_matrix(np.ones((1, 1))), num_epochs=2, verbose=False)         # 1 x 1: nothing can be applied
+    assert one.n_applied_ == 0
+
+
+@pytest.mark.parametrize("K", [1, 20, 33, 100])
+def test_wmf_any_k_and_ragged(oracle, K):
+    """K = 20 is the reference default (wmf.pyx:44): not a multiple of 32 -> FFMA Gram / GEMM kernels, VW = 1 lanes."""
+    import cymf_b200 as cymf
+    X = cymf.synth.synth_implicit(70, 45, 600, seed=K).tolil()
+    X[7, :] = 1                                                 # a dense row
+    X[0, :] = 0                                                 # a user without interactions
+    X[:, 1] = 0                                                 # an item without interactions
+    X = X.tocsr()
+    X.eliminate_zeros()
+    Wo, Ho = oracle.wmf_fit(X, K, 0.01, 10.0, 2)
+    # K = 100 exceeds both matrix dimensions: Y^T Y is rank deficient and only wd I keeps the systems regular
+    # (condition ~1e4), so the residual tolerance of 1e-10 leaves ~1e-6 in the f64 solution; the bar is 1e-4.
+    for dtype, tol in (("float64", 1e-8 if K < 45 else 1e-5), ("float32", 1e-4)):
+        m = cymf.WMF(K, 0.01, 10.0, dtype=dtype)
+        m.fit(X, 2, 1, verbose=False)
+        assert _rel(m.W, Wo) <= tol and _rel(m.H, Ho) <= tol, (dtype, _rel(m.W, Wo), _rel(m.H, Ho))
+        assert not m.W[0].any() and not m.H[1].any()
+    with pytest.raises(ValueError):
+        cymf.WMF(129)
+
+
+def test_wmf_solver_variants_agree(oracle):
+    """plain CG, G^-1-preconditioned CG and the Cholesky-transformed solver reach the same factors."""
+    import cymf_b200 as cymf
+    X = cymf.synth.synth_implicit(200, 150, 4000, seed=3)
+    Wo, Ho = oracle.wmf_fit(X, 64, 0.01, 10.0, 2)
+    for solver in ("cg", "pcg", "transformed"):
+        m = cymf.WMF(64, 0.01, 10.0, solver=solver)
+        m.fit(X, 2, 1, verbose=False)
+        assert _rel(m.W, Wo) <= 1e-4 and _rel(m.H, Ho) <= 1e-4, solver
+
+
+def test_glove_default_k_and_duplicates(oracle):
+    """K = 50 is the reference default (glove.pyx:58): rows are padded to 52; repeated (c, x) samples are legal."""
+    import cymf_b200 as cymf
+    rng = np.random.default_rng(1)
+    V, K, N = 30, 50, 300
+    c = rng.integers(0, V, N).astype(np.int32)
+    x = rng.integers(0, V, N).astype(np.int32)
+    c[10:20], x[10:20] = c[0], x[0]                            # duplicates
+    n = np.exp(rng.normal(0, 1.5, N)).clip(0.1) * 3
+    W0, H0 = rng.uniform(-.5, .5, (V, K)) / K, rng.uniform(-.5, .5, (V, K)) / K
+    b0, d0 = rng.uniform(-.5, .5, V) / K, rng.uniform(-.5, .5, V) / K
+    W, H, bw, bh = W0.copy(), H0.copy(), b0.copy(), d0.copy()
+    oracle.glove_fit(c, x, n, W, bw, H, bh, 2, 0.05, 10.0, 0.75)
+    g = cymf.GloVe(K, 0.05, 0.75, 10.0, mode="replay")
+    Wg, Hg, bwg, bhg = W0.copy(), H0.copy(), b0.copy(), d0.copy()
+    g._fit_glove(c, x, n, Wg, bwg, Hg, bhg, 2, 0.05, 10.0, 0.75, 1, False)
+    for got, want in ((Wg, W), (Hg, H), (bwg, bw), (bhg, bh)):
+        assert _rel(got, want) <= 1e-12
+    with pytest.raises(IndexError):
+        g._fit_glove(c + V, x, n, Wg, bwg, Hg, bhg, 1, 0.05, 10.0, 0.75, 1, False)
+
+
+def test_evaluator_extremes(oracle):
+    """num_negatives = 0, k larger than the candidate list, a user whose positives fill the catalogue but one item."""
+    import cymf_b200 as cymf
+    rng = np.random.default_rng(2)
+    A = (rng.random((15, 12)) < 0.4).astype(float)
+    A[3, :] = 1
+    A[3, 0] = 0
+    test = sparse.csr_matrix(A * (rng.random(A.shape) < 0.4))
+    train = sparse.csr_matrix(A) - test
+    train.eliminate_zeros()
+    W, H = rng.normal(size=(15, 6)), rng.normal(size=(12, 6))
+    for nneg, ks in ((0, [1, 5]), (7, [1, 50]), (100, 5)):
+        got = cymf.evaluator.Evaluator(test, train, k=ks, num_negatives=nneg).evaluate(W, H, 9)
+        want = oracle.evaluate(W, H, test, train, k=ks, num_negatives=nneg, seed=9)
+        assert set(got) == set(want)
+        for key in want:
+            assert abs(got[key] - want[key]) <= 1e-15, (nneg, key)
