@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "exp_table.h"
+#include "optim.cuh"
 
 namespace cymf {
 
@@ -28,30 +29,6 @@ template <typename T> struct BprArgs {
     uint32_t epoch;
     unsigned long long *applied;
 };
-
-__device__ __forceinline__ float sigmoid_neg(float x) { return __frcp_rn(1.0f + __expf(x)); }
-__device__ __forceinline__ double sigmoid_neg(double x) { return 1.0 / (1.0 + exp(x)); }
-__device__ __forceinline__ float rsqrt_t(float x) { return rsqrtf(x); }
-__device__ __forceinline__ double rsqrt_t(double x) { return 1.0 / sqrt(x); }
-__device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
-__device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
-
-// One row slot of the update rule; g is the reference's gradient (model.pyx:81-83), theta the pre-update value.
-// Returns the additive step d such that theta_new = theta + d, and advances the optimizer state in place.
-template <typename T, int OPT>
-__device__ __forceinline__ T opt_step(T g, T lr, T &s1, T &s2) {
-    if (OPT == CYMF_SGD) {
-        return -lr * g;                                           // optimizer.pyx:52-58
-    } else if (OPT == CYMF_ADAGRAD) {
-        s1 += g * g;                                              // optimizer.pyx:74-82 (state starts at 1)
-        return -lr * g * rsqrt_t(s1);
-    } else {
-        const T b1 = T(0.9), b2 = T(0.999), eps = T(1e-8);        // optimizer.pyx:127-160, no timestep
-        s1 = b1 * s1 + (T(1) - b1) * g;
-        s2 = b2 * s2 + (T(1) - b2) * g * g;
-        return -lr * (s1 / (T(1) - b1)) / (sqrt_t(s2 / (T(1) - b2)) + eps);
-    }
-}
 
 template <typename T, int OPT, int LPT, int NV, bool RED>
 __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const BprArgs<T> a) {

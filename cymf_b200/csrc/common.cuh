@@ -193,6 +193,29 @@ __device__ __forceinline__ bool group_contains(const int32_t *__restrict__ indic
     const bool mine = (lo + sub < hi) && (__ldg(indices + lo + sub) == key);
     return (__ballot_sync(gmask, mine) & gmask) != 0u;
 }
+// Position of `key` in the sorted run indices[lo, hi), or -1.  Same (LPT+1)-ary search as group_contains.
+template <int LPT>
+__device__ __forceinline__ int64_t group_find(const int32_t *__restrict__ indices, int64_t lo, int64_t hi, int32_t key,
+                                              int sub, unsigned gmask, int gshift) {
+    while (hi - lo > LPT) {
+        const int64_t span = hi - lo;
+        const int64_t p = lo + (span * (sub + 1)) / (LPT + 1);
+        const int32_t v = __ldg(indices + p);
+        const unsigned ge = (__ballot_sync(gmask, v >= key) & gmask) >> gshift;
+        const unsigned eq = (__ballot_sync(gmask, v == key) & gmask) >> gshift;
+        if (eq) { const int t = __ffs(eq) - 1; return lo + (span * (t + 1)) / (LPT + 1); }
+        if (ge == 0u) {
+            lo = lo + (span * LPT) / (LPT + 1) + 1;
+        } else {
+            const int t = __ffs(ge) - 1;
+            hi = lo + (span * (t + 1)) / (LPT + 1);
+            if (t > 0) lo = lo + (span * t) / (LPT + 1) + 1;
+        }
+    }
+    const bool mine = (lo + sub < hi) && (__ldg(indices + lo + sub) == key);
+    const unsigned hit = (__ballot_sync(gmask, mine) & gmask) >> gshift;
+    return hit ? lo + (__ffs(hit) - 1) : (int64_t)-1;
+}
 #endif  // __CUDACC__
 
 }  // namespace cymf
