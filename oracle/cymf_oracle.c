@@ -68,6 +68,25 @@ int64_t oracle_rng_below(oracle_rng *g, uint32_t n) {
     return (int64_t)(prod >> 32);
 }
 
+/* one draw of uniform_int_distribution<long>(0, n-1) for any n >= 1 (libstdc++ >= 11, bits/uniform_int_dist.h):
+ * ranges narrower than the 32-bit engine use the multiply-shift map above; a range of exactly 2^32 takes the raw
+ * word; wider ranges draw the high part recursively over [0, (n-1) / 2^32], add a raw low word and redraw
+ * while the sum exceeds n-1 (RelMF draws cells from [0, U*I), cymf/relmf.pyx:127). */
+int64_t oracle_rng_below64(oracle_rng *g, uint64_t n) {
+    const uint64_t urange = n - 1;
+    if (urange < 0xffffffffull) return oracle_rng_below(g, (uint32_t)n);
+    if (urange == 0xffffffffull) return (int64_t)oracle_rng_u32(g);
+    uint64_t ret, tmp;
+    do {
+        tmp = 0x100000000ull * (uint64_t)oracle_rng_below64(g, urange / 0x100000000ull + 1);
+        ret = tmp + (uint64_t)oracle_rng_u32(g);
+    } while (ret > urange || ret < tmp);
+    return (int64_t)ret;
+}
+void oracle_rng_fill_below64(oracle_rng *g, uint64_t n, int64_t *out, int64_t count) {
+    for (int64_t t = 0; t < count; ++t) out[t] = oracle_rng_below64(g, n);
+}
+
 oracle_rng *oracle_rng_new(uint32_t seed) {
     oracle_rng *g = (oracle_rng *)malloc(sizeof(oracle_rng));
     if (g) oracle_rng_seed(g, seed);
@@ -175,6 +194,98 @@ int oracle_bpr_fit(double *W, double *H, int32_t U, int32_t I, int32_t K,
             }
         }
         if (loss_out) loss_out[epoch] = accum / (double)N;                  /* bpr.pyx:171 */
+    }
+    free(sW1); free(sH1); free(sW2); free(sH2);
+    return 0;
+}
+
+/* position of `key` in the sorted run indices[lo, hi), or -1 */
+static int64_t row_find(const int32_t *indices, int64_t lo, int64_t hi, int32_t key) {
+    while (lo < hi) {
+        int64_t mid = lo + ((hi - lo) >> 1);
+        int32_t v = indices[mid];
+        if (v == key) return mid;
+        if (v < key) lo = mid + 1; else hi = mid;
+    }
+    return -1;
+}
+
+/* one element of the reference's optimizers (cymf/optimizer.pyx:52-58, 74-82, 150-160) */
+static void opt_update(double *theta, double g, double lr, int32_t optimizer, double *s1, double *s2) {
+    if (optimizer == 0) {
+        *theta -= lr * g;
+    } else if (optimizer == 1) {
+        *s1 += g * g;
+        *theta -= lr * g / sqrt(*s1);
+    } else {
+        const double beta1 = 0.9, beta2 = 0.999, eps = 1e-8;
+        *s1 = beta1 * *s1 + (1 - beta1) * g;
+        *s2 = beta2 * *s2 + (1 - beta2) * (g * g);
+        *theta -= lr * (*s1 / (1 - beta1)) / (sqrt(*s2 / (1 - beta2)) + eps);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * RelMF   (cymf/relmf.pyx:107-148, cymf/model.pyx:89-142; optimizers as for BPR)
+ *   Every epoch draws U*I cells r ~ U[0, U*I) from one mt19937(seed) that lives for the whole fit,
+ *   u = r / I, i = r % I (relmf.pyx:144-146); the label X[u,i] is read from the dense matrix in the
+ *   reference and from the CSR here (absent cell = 0.0, `values` NULL = all stored cells are 1.0).
+ *   t = W_u . H_i (k ascending); c = X[u,i] / max(p_i, clip);
+ *   g_w = -(c (1 - t) H_ik + (1 - c)(0 - t) H_ik) + wd W_uk, g_h symmetric, both from pre-update
+ *   values (model.pyx:129-141).
+ *   cells_in (num_epochs*n, may be NULL) replaces the mt19937 stream; cells_out records it;
+ *   loss_out (num_epochs, may be NULL) = accum_loss of relmf.pyx:150-152 (sum, not mean).
+ * ---------------------------------------------------------------------------------------------- */
+int oracle_relmf_fit(double *W, double *H, int32_t U, int32_t I, int32_t K,
+                     const int32_t *indptr, const int32_t *indices, const double *values,
+                     const double *propensities, int64_t n_samples,
+                     int32_t num_epochs, double lr, double wd, double clip, int32_t optimizer, uint32_t seed,
+                     const int64_t *cells_in, int64_t *cells_out, double *loss_out) {
+    double *sW1 = NULL, *sH1 = NULL, *sW2 = NULL, *sH2 = NULL;
+    size_t nW = (size_t)U * K, nH = (size_t)I * K;
+    if (optimizer == 1) {
+        sW1 = (double *)malloc(nW * sizeof(double));
+        sH1 = (double *)malloc(nH * sizeof(double));
+        if (!sW1 || !sH1) return -1;
+        for (size_t t = 0; t < nW; ++t) sW1[t] = 1.0;
+        for (size_t t = 0; t < nH; ++t) sH1[t] = 1.0;
+    } else if (optimizer == 2) {
+        sW1 = (double *)calloc(nW, sizeof(double));
+        sH1 = (double *)calloc(nH, sizeof(double));
+        sW2 = (double *)calloc(nW, sizeof(double));
+        sH2 = (double *)calloc(nH, sizeof(double));
+        if (!sW1 || !sH1 || !sW2 || !sH2) return -1;
+    }
+    oracle_rng gen;
+    oracle_rng_seed(&gen, seed);                                              /* relmf.pyx:127 */
+    const uint64_t cells = (uint64_t)U * (uint64_t)I;
+    for (int32_t epoch = 0; epoch < num_epochs; ++epoch) {
+        double accum = 0.0;
+        for (int64_t l = 0; l < n_samples; ++l) {
+            int64_t r = cells_in ? cells_in[(int64_t)epoch * n_samples + l]
+                                 : oracle_rng_below64(&gen, cells);         /* relmf.pyx:144 */
+            if (cells_out) cells_out[(int64_t)epoch * n_samples + l] = r;
+            int32_t u = (int32_t)(r / I), i = (int32_t)(r % I);               /* relmf.pyx:145-146 */
+            int64_t pos = row_find(indices, indptr[u], indptr[u + 1], i);
+            double x = pos < 0 ? 0.0 : (values ? values[pos] : 1.0);          /* X[u, i] */
+            double p = propensities[i];
+            double pm = p >= clip ? p : clip;                                 /* dmax, math.pxd:47-51 */
+            double *wu = W + (size_t)u * K, *hi = H + (size_t)i * K;
+            double t = 0.0, l2 = 0.0;
+            for (int32_t k = 0; k < K; ++k) {                                 /* model.pyx:114-116 */
+                t += wu[k] * hi[k];
+                l2 += wu[k] * wu[k] + hi[k] * hi[k];
+            }
+            accum += (x / pm) * ((1. - t) * (1. - t)) + (1 - x / pm) * (t * t) + wd * l2;   /* model.pyx:118 */
+            for (int32_t k = 0; k < K; ++k) {                                 /* model.pyx:129-141 */
+                double gw = -((x / pm) * (1. - t) * hi[k] + (1 - x / pm) * (0. - t) * hi[k]) + wd * wu[k];
+                double gh = -((x / pm) * (1. - t) * wu[k] + (1 - x / pm) * (0. - t) * wu[k]) + wd * hi[k];
+                size_t ow = (size_t)u * K + k, oh = (size_t)i * K + k;
+                opt_update(wu + k, gw, lr, optimizer, sW1 ? sW1 + ow : NULL, sW2 ? sW2 + ow : NULL);
+                opt_update(hi + k, gh, lr, optimizer, sH1 ? sH1 + oh : NULL, sH2 ? sH2 + oh : NULL);
+            }
+        }
+        if (loss_out) loss_out[epoch] = accum;
     }
     free(sW1); free(sH1); free(sW2); free(sH2);
     return 0;

@@ -4,6 +4,7 @@ Each function mirrors the reference call it restates (file:line under /root/refe
   bpr_fit      <- cymf/bpr.pyx:117-171  (`BPR._fit_bpr`, num_threads=1)
   als_half     <- cymf/wmf.pyx:136-174  (`WMF._als`)
   glove_fit    <- cymf/glove.pyx:117-156 (`GloVe._fit_glove`)
+  relmf_fit    <- cymf/relmf.pyx:107-148 (`RelMF._fit_relmf`, num_threads=1)
   evaluate     <- cymf/evaluator.pyx:57-139 (`Evaluator.evaluate`, unbiased=False)
   rng_*        <- cymf/math.pyx:12-18 (`UniformGenerator`)
 plus the Python prologues of `fit()` (seeded init + one-time shuffle), which are host logic shared
@@ -45,6 +46,12 @@ def lib():
                                         C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_uint32,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.oracle_rng_fill_below64.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64]
+        _lib.oracle_relmf_fit.restype = C.c_int
+        _lib.oracle_relmf_fit.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_uint32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.oracle_als_half.restype = C.c_int
         _lib.oracle_als_half.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_double]
@@ -95,6 +102,12 @@ class Rng:
         lib().oracle_rng_fill_below(self._h, n, _p(out), count)
         return out
 
+    def below64(self, n, count):
+        """any n >= 1, including ranges wider than the 32-bit engine (RelMF cells, cymf/relmf.pyx:127)"""
+        out = np.empty(count, np.int64)
+        lib().oracle_rng_fill_below64(self._h, n, _p(out), count)
+        return out
+
 
 def init_factors(U, I, K):
     """`fit()` prologue, cymf/bpr.pyx:97-101 == cymf/wmf.pyx:88-92 (both factors absent)."""
@@ -136,6 +149,40 @@ def bpr_fit(W, H, users, positives, X, num_epochs, lr, wd, optimizer="sgd", seed
     if rc:
         raise MemoryError("oracle_bpr_fit")
     return {"negatives": neg, "applied": app, "loss": ls}
+
+
+def relmf_propensities(X):
+    """cymf/relmf.pyx:90: sqrt of the relative item popularity, floored at 1e-5 (dense NumPy in the reference)."""
+    X = np.asarray(X.todense() if hasattr(X, "todense") else X, dtype=np.float64)
+    return np.maximum(X.mean(axis=0) / X.mean(axis=0).max(), 1e-5) ** 0.5
+
+
+def relmf_fit(W, H, X, num_epochs, lr, wd, clip, optimizer="adam", seed=1234, propensities=None,
+              cells=None, record=False, loss=False, n_samples=None):
+    """`RelMF._fit_relmf` (cymf/relmf.pyx:107-148), num_threads=1; in place on W, H."""
+    from scipy import sparse
+    assert W.dtype == np.float64 and H.dtype == np.float64 and W.flags.c_contiguous and H.flags.c_contiguous
+    Xs = sparse.csr_matrix(X).astype(np.float64)
+    Xs.sum_duplicates()
+    Xs.sort_indices()
+    U, I = Xs.shape
+    if propensities is None:
+        propensities = relmf_propensities(Xs)
+    propensities = np.ascontiguousarray(np.asarray(propensities).ravel(), np.float64)
+    n = int(U) * int(I) if n_samples is None else int(n_samples)
+    indptr = np.ascontiguousarray(Xs.indptr, np.int32)
+    indices = np.ascontiguousarray(Xs.indices, np.int32)
+    data = np.ascontiguousarray(Xs.data, np.float64)
+    rec = np.empty(num_epochs * n, np.int64) if record else None
+    ls = np.empty(num_epochs, np.float64) if loss else None
+    if cells is not None:
+        cells = np.ascontiguousarray(cells, np.int64)
+        assert cells.shape[0] == num_epochs * n
+    rc = lib().oracle_relmf_fit(_p(W), _p(H), U, I, W.shape[1], _p(indptr), _p(indices), _p(data), _p(propensities), n,
+                                num_epochs, lr, wd, clip, OPTIMIZERS[optimizer], seed, _p(cells), _p(rec), _p(ls))
+    if rc:
+        raise MemoryError("oracle_relmf_fit")
+    return {"cells": rec, "loss": ls}
 
 
 def als_half(indptr, indices, X, Y, wd, weight):

@@ -53,6 +53,42 @@ int main(){ std::mt19937 g(1234); for(int t=0;t<16;++t) printf("%u ", (unsigned)
     return out
 
 
+def rng64_vectors():
+    """uniform_int_distribution<long> over ranges at and beyond the 32-bit engine's (RelMF draws from [0, U*I))."""
+    ns = (3703857792, 4294967296, 4294967297, 5000000000, 10000000000000)
+    src = r"""
+#include <random>
+#include <cstdio>
+int main(){ long ns[5]={3703857792L,4294967296L,4294967297L,5000000000L,10000000000000L};
+ for(int q=0;q<5;++q){ std::mt19937 r(1234); std::uniform_int_distribution<long> d(0,ns[q]-1);
+  for(int t=0;t<96;++t) printf("%ld ", d(r)); printf("\n"); }
+ return 0; }
+"""
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "k.cpp")
+        open(p, "w").write(src)
+        subprocess.check_call(["/usr/bin/g++", "-O1", p, "-o", os.path.join(d, "k")])
+        lines = subprocess.check_output([os.path.join(d, "k")]).decode().strip().split("\n")
+    return {f"below_{n}_seed1234": np.array(lines[q].split(), dtype=np.int64) for q, n in enumerate(ns)}
+
+
+def relmf_case(U, I, nnz, K, epochs, lr, wd, clip, opt, seed, ratings=False):
+    """`RelMF.fit` of the compiled reference on a dense matrix (relmf.pyx:68-105 densifies sparse input anyway)."""
+    X = synth_implicit(U, I, nnz, seed).astype(np.float64)
+    if ratings:                                             # X[u,i] is used as a value, not only as a flag
+        X.data[:] = np.random.default_rng(seed).integers(1, 6, X.nnz) / 5.0
+    m = cymf.RelMF(K, clip, lr, opt, wd)
+    m.fit(X.toarray(), epochs, 1)
+    np.random.seed(4321)
+    W0 = np.random.uniform(low=-0.1, high=0.1, size=(U, K)) / K
+    H0 = np.random.uniform(low=-0.1, high=0.1, size=(I, K)) / K
+    dense = X.toarray()
+    prop = np.maximum(dense.mean(axis=0) / dense.mean(axis=0).max(), 1e-5) ** 0.5
+    return dict(indptr=X.indptr.astype(np.int32), indices=X.indices.astype(np.int32), data=X.data,
+                shape=np.array([U, I, K]), W0=W0, H0=H0, W=np.array(m.W), H=np.array(m.H), propensities=prop,
+                epochs=epochs, lr=lr, wd=wd, clip=clip, opt=opt)
+
+
 def bpr_case(U, I, nnz, K, epochs, lr, wd, opt, seed):
     from sklearn import utils
     X = synth_implicit(U, I, nnz, seed).astype(np.float64)
@@ -155,16 +191,25 @@ def metric_vectors():
 
 
 def main():
-    save = lambda name, d: np.savez_compressed(os.path.join(HERE, name), **d)  # noqa: E731
-    save("rng.npz", rng_vectors())
+    only = set(sys.argv[1:])                                # e.g. `make_golden.py relmf rng64` regenerates a subset
+
+    def save(name, make):
+        if not only or any(name.startswith(o) for o in only):
+            np.savez_compressed(os.path.join(HERE, name), **make())
+
+    save("rng64.npz", rng64_vectors)
     for opt in ("sgd", "adagrad", "adam"):
-        save(f"bpr_{opt}.npz", bpr_case(60, 90, 700, 20, 3, 0.01, 0.01, opt, seed=11))
-    save("bpr_sgd_mid.npz", bpr_case(300, 500, 12000, 16, 4, 0.05, 0.002, "sgd", seed=12))
-    save("wmf_small.npz", wmf_case(60, 90, 700, 8, 3, 0.01, 10.0, seed=21))
-    save("wmf_k64.npz", wmf_case(150, 120, 3000, 64, 2, 0.01, 10.0, seed=22))
-    save("glove.npz", glove_case(50, 400, 16, 3, 0.05, 10.0, 0.75, seed=31))
-    save("evaluator.npz", eval_case(120, 200, 4000, 12, seed=41))
-    save("metrics.npz", metric_vectors())
+        save(f"relmf_{opt}.npz", lambda: relmf_case(30, 40, 300, 12, 2, 0.05, 0.01, 0.1, opt, seed=51))
+    save("relmf_ratings.npz", lambda: relmf_case(25, 35, 260, 20, 2, 0.001, 0.01, 0.3, "adam", seed=52, ratings=True))
+    save("rng.npz", rng_vectors)
+    for opt in ("sgd", "adagrad", "adam"):
+        save(f"bpr_{opt}.npz", lambda: bpr_case(60, 90, 700, 20, 3, 0.01, 0.01, opt, seed=11))
+    save("bpr_sgd_mid.npz", lambda: bpr_case(300, 500, 12000, 16, 4, 0.05, 0.002, "sgd", seed=12))
+    save("wmf_small.npz", lambda: wmf_case(60, 90, 700, 8, 3, 0.01, 10.0, seed=21))
+    save("wmf_k64.npz", lambda: wmf_case(150, 120, 3000, 64, 2, 0.01, 10.0, seed=22))
+    save("glove.npz", lambda: glove_case(50, 400, 16, 3, 0.05, 10.0, 0.75, seed=31))
+    save("evaluator.npz", lambda: eval_case(120, 200, 4000, 12, seed=41))
+    save("metrics.npz", metric_vectors)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

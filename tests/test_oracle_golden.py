@@ -1,6 +1,6 @@
 """Pins oracle/cymf_oracle.c against vectors produced by the compiled reference (tests/golden/make_golden.py).
 
-BPR / GloVe: the oracle follows the reference's operation order exactly, so equality is bitwise.
+BPR / RelMF / GloVe: the oracle follows the reference's operation order exactly, so equality is bitwise.
 WMF: the reference's Gram is a BLAS dgemm and its solve a LAPACK dgesv (different summation order), so
 the bound is 1e-10 relative -- six orders below the 1e-4 the product is held to.
 Evaluator: metric means equal to 1e-15 (scores come from BLAS `np.dot` in the reference).
@@ -21,6 +21,28 @@ def test_rng_known_answers(oracle):
     for n in (1682, 26744, 7, 1000003):
         assert np.array_equal(oracle.Rng(1234).below(n, 64), g[f"below_{n}_seed1234"])
     assert np.array_equal(oracle.Rng(99).below(3, 200), g["below_3_seed99"])
+
+
+def test_rng_wide_ranges(oracle):
+    """Ranges at / beyond the engine's 2^32 (libstdc++'s raw-word and upscaling branches): RelMF draws cells
+    from [0, U*I) (cymf/relmf.pyx:127), 3.7e9 at the ml-20m shape and 1e13 at C5's."""
+    g = golden("rng64.npz")
+    for n in (3703857792, 4294967296, 4294967297, 5000000000, 10000000000000):
+        want = g[f"below_{n}_seed1234"]
+        assert np.array_equal(oracle.Rng(1234).below64(n, want.shape[0]), want), n
+        assert want.max() < n and want.min() >= 0
+
+
+@pytest.mark.parametrize("name", ["relmf_sgd", "relmf_adagrad", "relmf_adam", "relmf_ratings"])
+def test_relmf_bitwise(oracle, name):
+    g = golden(name + ".npz")
+    U, I, K = g["shape"]
+    X = sparse.csr_matrix((g["data"], g["indices"], g["indptr"]), shape=(U, I))
+    assert np.array_equal(oracle.relmf_propensities(X), g["propensities"])
+    W, H = g["W0"].copy(), g["H0"].copy()
+    oracle.relmf_fit(W, H, X, int(g["epochs"]), float(g["lr"]), float(g["wd"]), float(g["clip"]), str(g["opt"]))
+    assert np.array_equal(W, g["W"])
+    assert np.array_equal(H, g["H"])
 
 
 @pytest.mark.parametrize("name", ["bpr_sgd", "bpr_adagrad", "bpr_adam", "bpr_sgd_mid"])
