@@ -125,6 +125,30 @@ def time_bpr_device(train, users, positives, K, optimizer, steps, warmup, dtype=
     return sum(per_step), s.applied() - a0, s, per_step
 
 
+def time_relmf_device(train, K, optimizer, steps, warmup, hbm, samples, dtype="float32"):
+    """RelMF epochs of `samples` uniformly drawn cells (the reference draws U*I per epoch; a bounded count here)."""
+    import torch
+    from cymf_b200.relmf import RelmfSession, item_propensities
+    from cymf_b200.host import init_factors
+    W, H = init_factors(train.shape[0], train.shape[1], K)
+    s = RelmfSession(W, H, train, item_propensities(train.astype(np.float64)), optimizer, dtype=dtype,
+                     samples_per_epoch=samples)
+    for _ in range(warmup):
+        s.epoch(0.01, 0.01, 0.1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        s.epoch(0.01, 0.01, 0.1)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / steps
+    gbps = samples * s.bytes_per_update / sec / 1e9
+    return {"samples_per_s": samples / sec, "ms_per_epoch": 1e3 * sec, "samples_per_epoch": samples,
+            "cells": int(train.shape[0]) * int(train.shape[1]), "K": K, "optimizer": optimizer,
+            "algorithmic_GBps": gbps, "frac_of_hbm_peak": gbps / hbm}
+
+
 def time_bpr_e2e(train, users, positives, K, optimizer, steps, warmup, lr=LR, wd=WD):
     """Through the typed boundary with host buffers: every step uploads inputs and downloads the factors."""
     import torch
@@ -360,6 +384,9 @@ def main():
                           "algorithmic_GBps": a_ * ss.bytes_per_update / s_ / 1e9,
                           "frac_of_hbm_peak": a_ * ss.bytes_per_update / s_ / 1e9 / hbm}
             del ss
+            torch.cuda.empty_cache()
+        for tag, opt in (("relmf_sgd_f32_k128", "sgd"), ("relmf_adam_f32_k128", "adam")):
+            extra[tag] = time_relmf_device(train, 128, opt, max(3, args.steps // 2), 3, hbm, 50_000_000)
             torch.cuda.empty_cache()
     if not args.no_extra:
         # WMF ALS shards over the ranks (row blocks, all-gather + Gram all-reduce): every rank takes part

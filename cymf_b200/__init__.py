@@ -11,6 +11,7 @@ no CPU fallback -- calls raise when it has not been built or no CUDA device is v
 """
 from .bpr import BPR
 from .wmf import WMF
+from .relmf import RelMF
 from .glove import GloVe
 from . import evaluator
 from .evaluator import Evaluator, AverageOverAllEvaluator, AoaEvaluator, UnbiasedEvaluator

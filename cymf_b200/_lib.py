@@ -36,6 +36,15 @@ SIGNATURES = {
     "cymf_rng_create": (_p, [_u32]),
     "cymf_rng_destroy": (None, [_p]),
     "cymf_rng_fill_below": (C.c_int, [_p, _u32, _p, _i64]),
+    "cymf_rng_fill_below64": (C.c_int, [_p, _u64, _p, _i64]),
+    "cymf_convert_dev": (C.c_int, [_p, _p, C.c_int, _i64, _p]),
+    "cymf_relmf_hogwild_epoch_dev": (C.c_int, [C.POINTER(Factors), C.c_int, C.c_int, C.c_int, _p, _p, _p, _p,
+                                               _i32, _i32, _i32, _i32, _i64, _f64, _f64, _f64, _u64, _u32, _i64, _p]),
+    "cymf_relmf_cells_host": (C.c_int, [_u64, _u32, _i64, _i64, _i32, _i32, _p]),
+    "cymf_relmf_replay_epoch_dev": (C.c_int, [C.POINTER(Factors), C.c_int, _p, _i64, _p, _p, _p, _p,
+                                              _i32, _i32, _i32, _i32, _f64, _f64, _f64, _p]),
+    "cymf_relmf_fit_host": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _i32, _f64, _f64, _f64,
+                                      C.c_int, C.c_int, _u64]),
     "cymf_pack_rows_dev": (C.c_int, [_p, _p, C.c_int, _i64, _i32, _i32, _p]),
     "cymf_unpack_rows_dev": (C.c_int, [_p, _p, C.c_int, _i64, _i32, _i32, _p]),
     "cymf_fill_dev": (C.c_int, [_p, C.c_int, _i64, _f64, _p]),
@@ -138,6 +147,12 @@ class HostRng:
         import numpy as np
         out = np.empty(int(count), np.int32)
         check(lib().cymf_rng_fill_below(self._h, int(n), out.ctypes.data_as(C.c_void_p), int(count)))
+        return out
+
+    def below64(self, n, count):
+        import numpy as np
+        out = np.empty(int(count), np.int64)
+        check(lib().cymf_rng_fill_below64(self._h, int(n), out.ctypes.data_as(C.c_void_p), int(count)))
         return out
 
     def __del__(self):

@@ -149,11 +149,10 @@ class BprSession(object):
             self.d_applied = torch.zeros(1, dtype=torch.int64, device=dev)
         sp = [_lib.ptr(t) for t in self.state] + [None] * (4 - len(self.state))
         self.f = _lib.Factors(_lib.ptr(self.dW), _lib.ptr(self.dH), sp[0], sp[1], sp[2], sp[3])
-        # "auto": 128-bit red.global.add.v4.f32 costs the same as a vector store (measured) and loses no update;
-        # f64 reductions are scalar and 2.4x slower than stores, so f64 keeps plain stores.
-        self.scatter = {"auto": 1 if (opt == _lib.SGD and self.dtype == _lib.F32) else 0, "store": 0, "red": 1}[scatter]
-        if self.scatter and opt != _lib.SGD:
-            raise ValueError("scatter='red' is defined for the sgd optimizer only")
+        # "auto": 128-bit red.global.add.v4.f32 costs the same as a vector store (measured) and loses no update --
+        # parameters and optimizer state alike; f64 reductions are scalar and 2.4x slower than stores, so f64
+        # keeps plain stores.
+        self.scatter = {"auto": 1 if self.dtype == _lib.F32 else 0, "store": 0, "red": 1}[scatter]
         # bounds Hogwild staleness on small matrices; large ones fill the machine
         self.inflight = int(max_inflight) if max_inflight is not None else max(1024, N // 256)
         self.seed = int(seed)

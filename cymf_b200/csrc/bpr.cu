@@ -99,22 +99,35 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const BprArgs<T> a) {
                     const T gw = -(s * (hik - hjk) - a.wd * wk);                                      // model.pyx:81
                     const T gi = -(s * wk - a.wd * hik);                                              // model.pyx:82
                     const T gj = -(s * (-wk) - a.wd * hjk);                                           // model.pyx:83
-                    dw.v[e] = opt_step<T, OPT>(gw, a.lr, aw.v[e], bw.v[e]);
-                    di.v[e] = opt_step<T, OPT>(gi, a.lr, ai.v[e], bi.v[e]);
-                    dj.v[e] = opt_step<T, OPT>(gj, a.lr, aj.v[e], bj.v[e]);
+                    dw.v[e] = opt_step<T, OPT, RED>(gw, a.lr, aw.v[e], bw.v[e]);
+                    di.v[e] = opt_step<T, OPT, RED>(gi, a.lr, ai.v[e], bi.v[e]);
+                    dj.v[e] = opt_step<T, OPT, RED>(gj, a.lr, aj.v[e], bj.v[e]);
                     if (!RED) { dw.v[e] += wk; di.v[e] += hik; dj.v[e] += hjk; }
                 }
-                if (RED) { red_add_slot(pw + e0, dw); red_add_slot(pi + e0, di); red_add_slot(pj + e0, dj); }
-                else     { store_slot(pw + e0, dw);   store_slot(pi + e0, di);   store_slot(pj + e0, dj); }
-                if (OPT != CYMF_SGD) {
-                    store_slot(a.s1W + (size_t)u * a.ld + e0, aw);
-                    store_slot(a.s1H + (size_t)i * a.ld + e0, ai);
-                    store_slot(a.s1H + (size_t)j * a.ld + e0, aj);
-                }
-                if (OPT == CYMF_ADAM) {
-                    store_slot(a.s2W + (size_t)u * a.ld + e0, bw);
-                    store_slot(a.s2H + (size_t)i * a.ld + e0, bi);
-                    store_slot(a.s2H + (size_t)j * a.ld + e0, bj);
+                if (RED) {
+                    red_add_slot(pw + e0, dw); red_add_slot(pi + e0, di); red_add_slot(pj + e0, dj);
+                    if (OPT != CYMF_SGD) {
+                        red_add_slot(a.s1W + (size_t)u * a.ld + e0, aw);
+                        red_add_slot(a.s1H + (size_t)i * a.ld + e0, ai);
+                        red_add_slot(a.s1H + (size_t)j * a.ld + e0, aj);
+                    }
+                    if (OPT == CYMF_ADAM) {
+                        red_add_slot(a.s2W + (size_t)u * a.ld + e0, bw);
+                        red_add_slot(a.s2H + (size_t)i * a.ld + e0, bi);
+                        red_add_slot(a.s2H + (size_t)j * a.ld + e0, bj);
+                    }
+                } else {
+                    store_slot(pw + e0, dw); store_slot(pi + e0, di); store_slot(pj + e0, dj);
+                    if (OPT != CYMF_SGD) {
+                        store_slot(a.s1W + (size_t)u * a.ld + e0, aw);
+                        store_slot(a.s1H + (size_t)i * a.ld + e0, ai);
+                        store_slot(a.s1H + (size_t)j * a.ld + e0, aj);
+                    }
+                    if (OPT == CYMF_ADAM) {
+                        store_slot(a.s2W + (size_t)u * a.ld + e0, bw);
+                        store_slot(a.s2H + (size_t)i * a.ld + e0, bi);
+                        store_slot(a.s2H + (size_t)j * a.ld + e0, bj);
+                    }
                 }
             }
             if (sub == 0) ++n_applied;
@@ -260,10 +273,12 @@ static int dispatch_hogwild(const cymf_factors *f, int optimizer, int scatter, B
                            : dispatch_shape<T, CYMF_SGD, false>(a, max_groups, st);
         case CYMF_ADAGRAD:
             CYMF_REQUIRE(f->s1W && f->s1H, "adagrad needs s1W/s1H");
-            return dispatch_shape<T, CYMF_ADAGRAD, false>(a, max_groups, st);
+            return scatter ? dispatch_shape<T, CYMF_ADAGRAD, true>(a, max_groups, st)
+                           : dispatch_shape<T, CYMF_ADAGRAD, false>(a, max_groups, st);
         case CYMF_ADAM:
             CYMF_REQUIRE(f->s1W && f->s1H && f->s2W && f->s2H, "adam needs s1*/s2*");
-            return dispatch_shape<T, CYMF_ADAM, false>(a, max_groups, st);
+            return scatter ? dispatch_shape<T, CYMF_ADAM, true>(a, max_groups, st)
+                           : dispatch_shape<T, CYMF_ADAM, false>(a, max_groups, st);
     }
     set_error("bpr: unknown optimizer %d", optimizer);
     return CYMF_EINVAL;
@@ -282,7 +297,6 @@ extern "C" int cymf_bpr_hogwild_epoch_dev(const cymf_factors *f, int dtype, int 
                                           unsigned long long *applied, void *stream) {
     CYMF_REQUIRE(f && f->W && f->H && users && positives && indptr && indices, "null pointer");
     CYMF_REQUIRE(U > 0 && I > 0 && K > 0 && ld >= K && ld % 4 == 0, "bad shape (ld must be a multiple of 4, >= K)");
-    CYMF_REQUIRE(!scatter || optimizer == CYMF_SGD, "scatter=1 (red.add) is defined for SGD only");
     if (N <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == CYMF_F32) {

@@ -123,6 +123,18 @@ struct cymf_rng {
         }
         return (uint32_t)(m >> 32);
     }
+    // the same distribution over any n >= 1: a range of exactly 2^32 takes the raw word, wider ranges draw the
+    // high part recursively, add a raw low word and redraw while the sum leaves the range (libstdc++'s upscaling)
+    uint64_t below64(uint64_t n) {
+        const uint64_t top = n - 1;
+        if (top < 0xffffffffull) return below((uint32_t)n);
+        if (top == 0xffffffffull) return word();
+        for (;;) {
+            const uint64_t high = below64((top >> 32) + 1) << 32;
+            const uint64_t v = high + word();
+            if (v <= top && v >= high) return v;
+        }
+    }
 };
 
 extern "C" cymf_rng *cymf_rng_create(uint32_t seed) { return new (std::nothrow) cymf_rng(seed); }
@@ -130,6 +142,12 @@ extern "C" void cymf_rng_destroy(cymf_rng *g) { delete g; }
 extern "C" int cymf_rng_fill_below(cymf_rng *g, uint32_t n, int32_t *out, int64_t count) {
     CYMF_REQUIRE(g && out && n > 0 && count >= 0, "bad argument");
     for (int64_t t = 0; t < count; ++t) out[t] = (int32_t)g->below(n);
+    return 0;
+}
+
+extern "C" int cymf_rng_fill_below64(cymf_rng *g, uint64_t n, int64_t *out, int64_t count) {
+    CYMF_REQUIRE(g && out && n > 0 && count >= 0, "bad argument");
+    for (int64_t t = 0; t < count; ++t) out[t] = (int64_t)g->below64(n);
     return 0;
 }
 
@@ -171,6 +189,17 @@ extern "C" int cymf_fill_dev(void *dst, int dtype, int64_t n, double value, void
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == CYMF_F32) fill_kernel<float><<<grid_for(n), 256, 0, st>>>((float *)dst, n, (float)value);
     else fill_kernel<double><<<grid_for(n), 256, 0, st>>>((double *)dst, n, value);
+    CYMF_LAUNCHED();
+    return 0;
+}
+
+// dense f64 vector -> vector of `dtype` (propensities, X.data)
+extern "C" int cymf_convert_dev(const double *src, void *dst, int dtype, int64_t n, void *stream) {
+    CYMF_REQUIRE(src && dst && n >= 0, "bad argument");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CYMF_F32) pack_rows_kernel<float><<<grid_for(n), 256, 0, st>>>(src, (float *)dst, n, 1, 1);
+    else pack_rows_kernel<double><<<grid_for(n), 256, 0, st>>>(src, (double *)dst, n, 1, 1);
     CYMF_LAUNCHED();
     return 0;
 }
@@ -248,7 +277,7 @@ extern "C" int cymf_bpr_fit_host(double *W, double *H, int32_t U, int32_t I, int
             CYMF_CUDA(cudaStreamSynchronize(st));              // neg[] is reused by the next epoch
         }
     } else {
-        const int scatter = optimizer == CYMF_SGD ? 1 : 0;
+        const int scatter = dtype == CYMF_F32 ? 1 : 0;      // 128-bit reductions: parameters and optimizer state
         const int64_t inflight = N / 256 > 1024 ? N / 256 : 1024;
         for (int32_t epoch = 0; epoch < num_epochs; ++epoch)
             CYMF_TRY(cymf_bpr_hogwild_epoch_dev(&f, dtype, optimizer, scatter, d_users, d_pos, N, d_ip, d_idx, U, I, K,
@@ -263,5 +292,98 @@ extern "C" int cymf_bpr_fit_host(double *W, double *H, int32_t U, int32_t I, int
     CYMF_CUDA(cudaMemcpyAsync(&applied, d_applied, 8, cudaMemcpyDeviceToHost, st));
     CYMF_CUDA(cudaStreamSynchronize(st));
     if (applied_out) *applied_out = (int64_t)applied;
+    return 0;
+}
+
+// ---- host-buffer RelMF fit -------------------------------------------------------------------------------------
+extern "C" int cymf_relmf_fit_host(double *W, double *H, int32_t U, int32_t I, int32_t K,
+                                   const int32_t *indptr, const int32_t *indices, const double *values,
+                                   const double *propensities, int32_t num_epochs, double learning_rate,
+                                   double weight_decay, double clip_value, int optimizer, int mode, uint64_t seed) {
+    CYMF_REQUIRE(W && H && indptr && indices && propensities, "null pointer");
+    CYMF_REQUIRE(U > 0 && I > 0 && K > 0 && num_epochs >= 0, "bad shape");
+    CYMF_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (hogwild f32), 1 (hogwild f64) or 2 (replay f64)");
+    CYMF_REQUIRE(optimizer >= CYMF_SGD && optimizer <= CYMF_ADAM, "unknown optimizer");
+    int ndev = 0;
+    CYMF_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) { set_error("no CUDA device: cymf_b200 has no CPU fallback"); return CYMF_EUNSUPPORTED; }
+
+    const int dtype = mode == 0 ? CYMF_F32 : CYMF_F64;
+    const size_t es = dtype == CYMF_F32 ? 4 : 8;
+    const int32_t ld = (K + 3) / 4 * 4;
+    const int64_t nnz = indptr[U];
+    const int64_t n_samples = (int64_t)U * I;                   // relmf.pyx:121: N = U * I cells per epoch
+    DeviceArena mem;
+    cudaStream_t st = nullptr;
+
+    double *stage = nullptr;
+    int64_t big = (int64_t)(U > I ? U : I) * K;
+    if (big < nnz) big = nnz;
+    CYMF_TRY(mem.get(&stage, (size_t)big * 8));
+    cymf_factors f{};
+    CYMF_TRY(mem.get((char **)&f.W, (size_t)U * ld * es));
+    CYMF_TRY(mem.get((char **)&f.H, (size_t)I * ld * es));
+    CYMF_CUDA(cudaMemcpyAsync(stage, W, (size_t)U * K * 8, cudaMemcpyHostToDevice, st));
+    CYMF_TRY(cymf_pack_rows_dev(stage, f.W, dtype, U, K, ld, st));
+    CYMF_CUDA(cudaMemcpyAsync(stage, H, (size_t)I * K * 8, cudaMemcpyHostToDevice, st));
+    CYMF_TRY(cymf_pack_rows_dev(stage, f.H, dtype, I, K, ld, st));
+    if (optimizer != CYMF_SGD) {                               // state rebuilt on every fit (relmf.pyx:129-137)
+        const double init = optimizer == CYMF_ADAGRAD ? 1.0 : 0.0;
+        CYMF_TRY(mem.get((char **)&f.s1W, (size_t)U * ld * es));
+        CYMF_TRY(mem.get((char **)&f.s1H, (size_t)I * ld * es));
+        CYMF_TRY(cymf_fill_dev(f.s1W, dtype, (int64_t)U * ld, init, st));
+        CYMF_TRY(cymf_fill_dev(f.s1H, dtype, (int64_t)I * ld, init, st));
+        if (optimizer == CYMF_ADAM) {
+            CYMF_TRY(mem.get((char **)&f.s2W, (size_t)U * ld * es));
+            CYMF_TRY(mem.get((char **)&f.s2H, (size_t)I * ld * es));
+            CYMF_TRY(cymf_fill_dev(f.s2W, dtype, (int64_t)U * ld, 0.0, st));
+            CYMF_TRY(cymf_fill_dev(f.s2H, dtype, (int64_t)I * ld, 0.0, st));
+        }
+    }
+    int32_t *d_idx, *d_ip32;
+    int64_t *d_ip, *d_cells = nullptr;
+    char *d_val = nullptr, *d_prop;
+    CYMF_TRY(mem.get(&d_idx, (size_t)nnz * 4));
+    CYMF_TRY(mem.get(&d_ip32, (size_t)(U + 1) * 4));
+    CYMF_TRY(mem.get(&d_ip, (size_t)(U + 1) * 8));
+    CYMF_TRY(mem.get(&d_prop, (size_t)I * es));
+    CYMF_CUDA(cudaMemcpyAsync(d_idx, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+    CYMF_CUDA(cudaMemcpyAsync(d_ip32, indptr, (size_t)(U + 1) * 4, cudaMemcpyHostToDevice, st));
+    widen_indptr_kernel<<<grid_for(U + 1), 256, 0, st>>>(d_ip32, d_ip, U + 1);
+    CYMF_LAUNCHED();
+    // 1-column "matrices": pack converts f64 -> dtype
+    CYMF_CUDA(cudaMemcpyAsync(stage, propensities, (size_t)I * 8, cudaMemcpyHostToDevice, st));
+    CYMF_TRY(cymf_convert_dev(stage, d_prop, dtype, I, st));
+    if (values && nnz > 0) {
+        CYMF_TRY(mem.get(&d_val, (size_t)nnz * es));
+        CYMF_CUDA(cudaMemcpyAsync(stage, values, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+        CYMF_TRY(cymf_convert_dev(stage, d_val, dtype, nnz, st));
+    }
+
+    if (mode == 2) {
+        CYMF_TRY(mem.get(&d_cells, (size_t)n_samples * 8));
+        cymf_rng gen((uint32_t)seed);                          // relmf.pyx:127: one generator for the whole fit
+        std::vector<int64_t> cells((size_t)n_samples);
+        for (int32_t epoch = 0; epoch < num_epochs; ++epoch) {
+            for (int64_t t = 0; t < n_samples; ++t) cells[(size_t)t] = (int64_t)gen.below64((uint64_t)n_samples);
+            CYMF_CUDA(cudaMemcpyAsync(d_cells, cells.data(), (size_t)n_samples * 8, cudaMemcpyHostToDevice, st));
+            CYMF_TRY(cymf_relmf_replay_epoch_dev(&f, optimizer, d_cells, n_samples, d_ip, d_idx, (const double *)d_val,
+                                                 (const double *)d_prop, U, I, K, ld, learning_rate, weight_decay,
+                                                 clip_value, st));
+            CYMF_CUDA(cudaStreamSynchronize(st));
+        }
+    } else {
+        const int scatter = dtype == CYMF_F32 ? 1 : 0;      // 128-bit reductions: parameters and optimizer state
+        const int64_t inflight = n_samples / 256 > 1024 ? n_samples / 256 : 1024;
+        for (int32_t epoch = 0; epoch < num_epochs; ++epoch)
+            CYMF_TRY(cymf_relmf_hogwild_epoch_dev(&f, dtype, optimizer, scatter, d_ip, d_idx, d_val, d_prop, U, I, K, ld,
+                                                  n_samples, learning_rate, weight_decay, clip_value, seed,
+                                                  (uint32_t)epoch, inflight, st));
+    }
+    CYMF_TRY(cymf_unpack_rows_dev(f.W, stage, dtype, U, K, ld, st));
+    CYMF_CUDA(cudaMemcpyAsync(W, stage, (size_t)U * K * 8, cudaMemcpyDeviceToHost, st));
+    CYMF_TRY(cymf_unpack_rows_dev(f.H, stage, dtype, I, K, ld, st));
+    CYMF_CUDA(cudaMemcpyAsync(H, stage, (size_t)I * K * 8, cudaMemcpyDeviceToHost, st));
+    CYMF_CUDA(cudaStreamSynchronize(st));
     return 0;
 }

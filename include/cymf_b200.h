@@ -6,6 +6,7 @@
  *
  *   cymf_rng_*          <- cymf/math.pyx:12-18      UniformGenerator (std::mt19937 + uniform_int_distribution)
  *   cymf_bpr_*          <- cymf/bpr.pyx:117-171     BPR._fit_bpr      (+ cymf/model.pyx:47-87, cymf/optimizer.pyx)
+ *   cymf_relmf_*        <- cymf/relmf.pyx:107-148   RelMF._fit_relmf  (+ cymf/model.pyx:99-142, cymf/optimizer.pyx)
  *   cymf_glove_*        <- cymf/glove.pyx:117-156   GloVe._fit_glove  (+ cymf/model.pyx:166-204, optimizer.pyx:85-123)
  *   cymf_als_*, cymf_gram_* <- cymf/wmf.pyx:136-174 WMF._als          (+ cymf/linalg.pyx:144-163 solvep)
  *   cymf_eval_*         <- cymf/evaluator.pyx:57-139 Evaluator.evaluate (+ cymf/metrics.pyx:24-125)
@@ -50,6 +51,9 @@ cymf_rng *cymf_rng_create(uint32_t seed);
 void cymf_rng_destroy(cymf_rng *g);
 /* `count` draws of uniform_int_distribution<long>(0, n-1)(mt19937), libstdc++ >= 11 semantics */
 int cymf_rng_fill_below(cymf_rng *g, uint32_t n, int32_t *out, int64_t count);
+/* the same distribution for any n >= 1, including ranges wider than the 32-bit engine (RelMF draws cells from
+ * [0, U*I), cymf/relmf.pyx:127: 3.7e9 at the ml-20m shape) */
+int cymf_rng_fill_below64(cymf_rng *g, uint64_t n, int64_t *out, int64_t count);
 
 /* ---- layout helpers (device pointers) ------------------------------------------------------------------
  * The reference keeps W/H as dense f64 [rows, K] NumPy arrays (cymf/bpr.pyx:99-101).  On the device a
@@ -58,6 +62,8 @@ int cymf_rng_fill_below(cymf_rng *g, uint32_t n, int32_t *out, int64_t count);
 int cymf_pack_rows_dev(const double *src, void *dst, int dtype, int64_t rows, int32_t K, int32_t ld, void *stream);
 int cymf_unpack_rows_dev(const void *src, double *dst, int dtype, int64_t rows, int32_t K, int32_t ld, void *stream);
 int cymf_fill_dev(void *dst, int dtype, int64_t n, double value, void *stream);
+/* dense f64 device vector -> device vector of `dtype` (propensities, X.data) */
+int cymf_convert_dev(const double *src, void *dst, int dtype, int64_t n, void *stream);
 
 /* ---- BPR (cymf/bpr.pyx:160-171) -------------------------------------------------------------------- */
 /* Optimizer state: AdaGrad uses s1 (accumulators, init 1); Adam uses s1 = M, s2 = V (init 0); SGD none. */
@@ -71,8 +77,9 @@ typedef struct {
 /* One Hogwild epoch over the N shuffled (user, positive) pairs (bpr.pyx:162-169): one lane group per
  * triplet, negative j ~ U[0, I) from Philox4x32-10 keyed by (seed, epoch, l), skipped (not resampled)
  * when j is a positive of u (bpr.pyx:166-167), lock-free read-modify-write of the three rows.
- * `scatter`: 0 = plain vector stores (races lose updates, as in the reference), 1 = additive updates are
- * applied with red.global.add (SGD only).  `max_inflight` > 0 caps the number of triplets processed
+ * `scatter`: 0 = plain vector stores (races lose updates, as in the reference), 1 = the parameter step and
+ * the optimizer-state increments (AdaGrad: g^2; Adam: the m and v deltas) are applied with red.global.add, so
+ * no concurrent triplet of a row is lost.  `max_inflight` > 0 caps the number of triplets processed
  * concurrently (bounds Hogwild staleness on small matrices; 0 = fill the machine).
  * `applied` (device uint64, may be NULL) += accepted triplets. */
 int cymf_bpr_hogwild_epoch_dev(const cymf_factors *f, int dtype, int optimizer, int scatter,
@@ -107,6 +114,41 @@ int cymf_bpr_fit_host(double *W, double *H, int32_t U, int32_t I, int32_t K,
                       const int32_t *indptr, const int32_t *indices,
                       int32_t num_epochs, double learning_rate, double weight_decay,
                       int optimizer, int mode, uint64_t seed, int64_t *applied_out);
+
+/* ---- RelMF (cymf/relmf.pyx:143-148, cymf/model.pyx:99-142) ----------------------------------------------- */
+/* One Hogwild epoch of `n_samples` uniformly drawn cells (the reference draws U*I per epoch, relmf.pyx:121,143):
+ * sample l touches (u, i) ~ U[0,U) x U[0,I) from Philox4x32-10 keyed by (seed, epoch, l) -- the distribution of
+ * the reference's r ~ U[0, U*I), u = r / I, i = r % I.  The label X[u,i] is looked up in the CSR (`values` in
+ * CSR order with the element type of `dtype`, NULL = every stored cell is 1; absent cell = 0), the reference
+ * reads its densified copy (relmf.pyx:79-80).  propensities: [I] of `dtype` (relmf.pyx:90).  `factors` and
+ * `max_inflight` as for cymf_bpr_hogwild_epoch_dev.  `scatter` = 1 applies the parameter step and the
+ * optimizer-state increments (AdaGrad: g^2; Adam: the m and v deltas) with red.global.add for every optimizer,
+ * so no concurrent sample of a row is lost and Adam's (m, v) pair cannot be torn; 0 = plain stores. */
+int cymf_relmf_hogwild_epoch_dev(const cymf_factors *f, int dtype, int optimizer, int scatter,
+                                 const int64_t *indptr, const int32_t *indices, const void *values,
+                                 const void *propensities, int32_t U, int32_t I, int32_t K, int32_t ld,
+                                 int64_t n_samples, double learning_rate, double weight_decay, double clip_value,
+                                 uint64_t seed, uint32_t epoch, int64_t max_inflight, void *stream);
+
+/* The cells r = u * I + i the Hogwild kernel draws for samples first .. first+count-1 of `epoch` (host-side
+ * evaluation of the same code), so that a run can be audited against the CPU oracle. */
+int cymf_relmf_cells_host(uint64_t seed, uint32_t epoch, int64_t first, int64_t count, int32_t U, int32_t I,
+                          int64_t *out);
+
+/* Serialized f64 replay of one epoch with a caller-supplied cell stream (device int64[n_samples], r = u*I + i,
+ * e.g. from cymf_rng_fill_below64): samples applied strictly in order with the reference's operation order. */
+int cymf_relmf_replay_epoch_dev(const cymf_factors *f, int optimizer, const int64_t *cells, int64_t n_samples,
+                                const int64_t *indptr, const int32_t *indices, const double *values,
+                                const double *propensities, int32_t U, int32_t I, int32_t K, int32_t ld,
+                                double learning_rate, double weight_decay, double clip_value, void *stream);
+
+/* Host-buffer form of RelMF._fit_relmf(X, propensities, num_epochs, ...) (relmf.pyx:107-113) with X handed over as
+ * host CSR (int32 indptr / indices, f64 values or NULL) instead of the reference's dense U x I array; W, H dense
+ * f64 HOST arrays updated in place; U*I samples per epoch; mode as in cymf_bpr_fit_host. */
+int cymf_relmf_fit_host(double *W, double *H, int32_t U, int32_t I, int32_t K,
+                        const int32_t *indptr, const int32_t *indices, const double *values,
+                        const double *propensities, int32_t num_epochs, double learning_rate,
+                        double weight_decay, double clip_value, int optimizer, int mode, uint64_t seed);
 
 /* ---- GloVe (cymf/glove.pyx:149-156, cymf/model.pyx:166-204, cymf/optimizer.pyx:85-123) ---------------- */
 typedef struct {

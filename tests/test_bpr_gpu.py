@@ -105,16 +105,39 @@ def test_hogwild_kernel_one_triplet_at_a_time(oracle, opt, K):
     assert np.abs(m.H - H).max() <= 1e-12 * np.abs(H).max()
 
 
-def test_hogwild_red_scatter_equals_store_when_serial(oracle):
+@pytest.mark.parametrize("opt", ["sgd", "adagrad", "adam"])
+def test_hogwild_red_scatter_equals_store_when_serial(oracle, opt):
+    """scatter='red' (parameter steps and optimizer-state increments applied with red.global.add) is the same update
+    as plain stores when one triplet is in flight."""
     import cymf_b200 as cymf
     X = cymf.synth.synth_implicit(80, 120, 1500, seed=3)
     out = []
     for scatter in ("store", "red"):
-        m = cymf.BPR(64, 0.05, "sgd", 0.01, dtype="float64", scatter=scatter, max_inflight=1)
+        m = cymf.BPR(64, 0.05, opt, 0.01, dtype="float64", scatter=scatter, max_inflight=1)
         m.fit(X, num_epochs=2, verbose=False)
         out.append((m.W.copy(), m.H.copy()))
-    assert np.abs(out[0][0] - out[1][0]).max() <= 1e-13
-    assert np.abs(out[0][1] - out[1][1]).max() <= 1e-13
+    assert np.abs(out[0][0] - out[1][0]).max() <= 1e-11
+    assert np.abs(out[0][1] - out[1][1]).max() <= 1e-11
+
+
+@pytest.mark.parametrize("opt,lr,floor", [("adagrad", 0.05, 0.95), ("adam", 0.01, 0.75)])
+def test_hogwild_state_survives_heavy_collisions(oracle, opt, lr, floor):
+    """943 user rows with ~40 triplets of each in flight (max_inflight=0 fills the machine; the default cap is 1024
+    triplets): with reductions on the optimizer state and Adam's serial-bound clamp the factors stay finite.  AdaGrad
+    ranks as well as the reference; Adam, whose first moment is advanced by 40 stale increments at once, keeps
+    80 % of the reference's metrics (measured) where plain stores diverge to inf."""
+    import cymf_b200 as cymf
+    train, test = cymf.synth.movielens_like("ml-100k")
+    Xc, W, H, users, positives = oracle.bpr_prologue(train, 20)
+    oracle.bpr_fit(W, H, users, positives, Xc, 20, lr, 0.01, opt)
+    want = _mean_metrics(oracle, W, H, test, train)
+    m = cymf.BPR(20, lr, opt, 0.01, max_inflight=0)
+    m.fit(train, num_epochs=20, verbose=False)
+    assert np.isfinite(m.W).all() and np.isfinite(m.H).all()
+    got = _mean_metrics(oracle, m.W, m.H, test, train)
+    print(opt, "reference", want, "gpu, machine-filling concurrency", got)
+    for k in want:
+        assert got[k] >= floor * want[k], (k, got[k], want[k])
 
 
 def test_validation_on_device_equals_host_path():
