@@ -61,6 +61,16 @@ SIGNATURES = {
                                               _p, _p]),
     "cymf_glove_fit_host": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _f64, _f64, _f64,
                                       C.c_int, _p]),
+    "cymf_scan_workspace_bytes": (_i64, [_i64]),
+    "cymf_exclusive_scan_u32_dev": (C.c_int, [_p, _p, _i64, _p, _p]),
+    "cymf_sort_workspace_bytes": (_i64, [_i64]),
+    "cymf_sort_pairs_dev": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
+    "cymf_csr_transpose_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "cymf_csr_transpose_dev": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "cymf_deal_workspace_bytes": (_i64, [_i64]),
+    "cymf_deal_rows_dev": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _p]),
+    "cymf_csr_block_workspace_bytes": (_i64, [_i64]),
+    "cymf_csr_block_dev": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _p, _p]),
     "cymf_gram_workspace_doubles": (_i64, [_i64, _i32]),
     "cymf_gram_dev": (C.c_int, [_p, C.c_int, _i64, _i32, _i32, _f64, C.c_int, _p, _i64, _p, _p, _p]),
     "cymf_gram_finalize_dev": (C.c_int, [_p, C.c_int, _i32, _i32, _f64, _p, _p]),

@@ -37,7 +37,8 @@ class WMF(object):
     """
 
     def __init__(self, num_components=20, weight_decay=0.01, weight=10.0, *, dtype="float32", cg_tol=None,
-                 cg_max_iter=None, device=None, distributed="auto", peer_gather=True, solver="transformed"):
+                 cg_max_iter=None, device=None, distributed="auto", peer_gather=True, solver="transformed",
+                 prep="device"):
         self.num_components = int(num_components)
         self.weight_decay = float(weight_decay)
         self.weight = float(weight)
@@ -54,6 +55,9 @@ class WMF(object):
         self.distributed = distributed
         self.peer_gather = peer_gather
         self.solver = solver
+        if prep not in ("device", "host"):
+            raise ValueError("prep must be 'device' or 'host'")
+        self.prep = prep                 # where X^T, the row deal and the relabelled blocks are built
         self.cg_iterations_ = 0          # CG iterations summed over rows, last fit
         self.cg_unconverged_ = 0         # rows that stopped at cg_max_iter, last fit
 
@@ -100,7 +104,7 @@ class WMF(object):
         tol, iters = self._tolerances()
         sess = AlsSession(X, self.W, self.H, self.weight_decay, self.weight, dtype=self.dtype, cg_tol=tol,
                           cg_max_iter=iters, device=self.device, distributed=self.distributed,
-                          peer_gather=self.peer_gather, solver=self.solver)
+                          peer_gather=self.peer_gather, solver=self.solver, prep=self.prep)
         # how solved blocks reach the other ranks: "single" | "peer-store" (fused into the GEMM epilogue) | "nccl"
         self.gather_mode_ = "peer-store" if sess.peer else ("nccl" if sess.dist else "single")
         run_epochs(self, sess, num_epochs, sess.epoch, verbose, ncols=100)
@@ -150,8 +154,9 @@ class AlsSession(object):
     """Device-resident state of one `_fit_als` call (both CSR orientations of this rank's row blocks, full
     replicas of W and H in dealt order); `epoch()` = user half sweep + item half sweep (wmf.pyx:111-112)."""
 
-    def __init__(self, X, W, H, weight_decay, weight, *, dtype="float32", cg_tol=1e-6, cg_max_iter=128, device=None,
-                 distributed="auto", stage_rows=0, force_width=0, solver="transformed", peer_gather=True):
+    def __init__(self, X, W, H, weight_decay, weight, *, K=None, dtype="float32", cg_tol=1e-6, cg_max_iter=128, device=None,
+                 distributed="auto", stage_rows=0, force_width=0, solver="transformed", peer_gather=True,
+                 prep="device"):
         torch = _lib.require_cuda()
         self.peer_error = None
         self._unperm = {}
@@ -168,31 +173,21 @@ class AlsSession(object):
         self.dev = dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.dtype = _lib.DTYPES[dtype]
         self.tdt = tdt = torch.float32 if self.dtype == _lib.F32 else torch.float64
-        self.K = K = W.shape[1]
+        self.K = K = int(K if K is not None else W.shape[1])
         self.ld = ld = _lib.ld_for(K)
         self.wd, self.weight = float(weight_decay), float(weight)
         self.cg_tol, self.cg_max_iter, self.stage_rows = float(cg_tol), int(cg_max_iter), int(stage_rows)
-        X = X.tocsr()
-        self.U, self.I = U, I = X.shape
-        XT = X.T.tocsr()
-        # dealt (permuted + padded) index spaces of users and items
-        self.slot_u, self.Ru = _deal(np.diff(X.indptr), self.world)
-        self.slot_i, self.Ri = _deal(np.diff(XT.indptr), self.world)
-        new_u = np.empty(U, np.int64); new_u[self.slot_u[self.slot_u >= 0]] = np.flatnonzero(self.slot_u >= 0)
-        new_i = np.empty(I, np.int64); new_i[self.slot_i[self.slot_i >= 0]] = np.flatnonzero(self.slot_i >= 0)
-        Up, Ip = self.slot_u.shape[0], self.slot_i.shape[0]
-        lo_u, lo_i = self.rank * self.Ru, self.rank * self.Ri
-        blk_u = _relabel(X, self.slot_u[lo_u:lo_u + self.Ru], new_i, Ip)
-        blk_i = _relabel(XT, self.slot_i[lo_i:lo_i + self.Ri], new_u, Up)
-        self.nnz = int(X.nnz)
-        self.block_nnz = (int(blk_u.nnz), int(blk_i.nnz))
-        self.classes_u = self._classes(blk_u)
-        self.classes_i = self._classes(blk_i)
+        self.prep = prep
         with torch.cuda.device(dev):
-            def up(a, dt):
-                return torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev, non_blocking=True)
-            self.csr_u = (up(blk_u.indptr, np.int64), up(blk_u.indices, np.int32))
-            self.csr_i = (up(blk_i.indptr, np.int64), up(blk_i.indices, np.int32))
+            if prep == "device":
+                blk_u, blk_i = self._prepare_on_device(X)
+            else:
+                blk_u, blk_i = self._prepare_on_host(X)
+            self.csr_u, self.csr_i = blk_u, blk_i
+            self.block_nnz = (int(blk_u[1].numel()), int(blk_i[1].numel()))
+            self.classes_u = self._classes(blk_u[0])
+            self.classes_i = self._classes(blk_i[0])
+            U, I, Up, Ip = self.U, self.I, self.slot_u.shape[0], self.slot_i.shape[0]
             self.order_u = torch.arange(self.Ru, dtype=torch.int32, device=dev)
             self.order_i = torch.arange(self.Ri, dtype=torch.int32, device=dev)
             self.dW = self._upload(W, self.slot_u)
@@ -213,8 +208,64 @@ class AlsSession(object):
             self.queue = torch.zeros(1, dtype=torch.int32, device=dev)
             self.d_stats = torch.zeros(2, dtype=torch.int64, device=dev)
         self.epochs_done = 0
-        self.h2d_bytes = W.nbytes + H.nbytes + 8 * (self.Ru + self.Ri + 2) + 4 * (blk_u.nnz + blk_i.nnz)
-        self.d2h_bytes = W.nbytes + H.nbytes
+        self.h2d_bytes = self._nbytes(W) + self._nbytes(H) + 8 * (self.Ru + self.Ri + 2) + 4 * sum(self.block_nnz)
+        self.d2h_bytes = self._nbytes(W) + self._nbytes(H)
+
+    @staticmethod
+    def _nbytes(a):
+        return int(a.nbytes) if isinstance(a, np.ndarray) else int(a.numel() * a.element_size())
+
+    def _prepare_on_host(self, X):
+        """scipy / NumPy construction of this rank's row blocks (the reference's own tools: `X.T.tocsr()`,
+        wmf.pyx:112).  Kept as the checker of the device path and for the gloo CPU tests."""
+        import torch
+        dev = self.dev
+        X = X.tocsr()
+        self.U, self.I = U, I = X.shape
+        XT = X.T.tocsr()
+        # dealt (permuted + padded) index spaces of users and items
+        self.slot_u, self.Ru = _deal(np.diff(X.indptr), self.world)
+        self.slot_i, self.Ri = _deal(np.diff(XT.indptr), self.world)
+        new_u = np.empty(U, np.int64); new_u[self.slot_u[self.slot_u >= 0]] = np.flatnonzero(self.slot_u >= 0)
+        new_i = np.empty(I, np.int64); new_i[self.slot_i[self.slot_i >= 0]] = np.flatnonzero(self.slot_i >= 0)
+        Up, Ip = self.slot_u.shape[0], self.slot_i.shape[0]
+        lo_u, lo_i = self.rank * self.Ru, self.rank * self.Ri
+        blk_u = _relabel(X, self.slot_u[lo_u:lo_u + self.Ru], new_i, Ip)
+        blk_i = _relabel(XT, self.slot_i[lo_i:lo_i + self.Ri], new_u, Up)
+        self.nnz = int(X.nnz)
+        self.d_slot_u, self.d_slot_i = (torch.from_numpy(a).to(dev) for a in (self.slot_u, self.slot_i))
+        self.d_row_slot_u, self.d_row_slot_i = torch.from_numpy(new_u).to(dev), torch.from_numpy(new_i).to(dev)
+
+        def up(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev, non_blocking=True)
+        return (up(blk_u.indptr, np.int64), up(blk_u.indices, np.int32)), (up(blk_i.indptr, np.int64), up(blk_i.indices, np.int32))
+
+    def _prepare_on_device(self, X):
+        """The same construction with cymf_b200/csrc/prep.cu: the CSR is uploaded once (or already lives on the
+        device: X = (indptr int64 tensor, indices int32 tensor, (U, I))), transpose / deal / relabel run as kernels."""
+        import torch
+        from . import prep
+        dev = self.dev
+        if isinstance(X, tuple):
+            ip, ix, (U, I) = X
+            ip, ix = ip.to(dev), ix.to(dev)
+        else:
+            X = X.tocsr()
+            U, I = X.shape
+            ip = torch.from_numpy(X.indptr.astype(np.int64)).to(dev)
+            ix = torch.from_numpy(np.ascontiguousarray(X.indices, np.int32)).to(dev)
+        self.U, self.I = int(U), int(I)
+        self.nnz = int(ix.numel())
+        t_ip, t_ix = prep.transpose_csr(ip, ix, self.U, self.I)
+        slot_u, row_slot_u, self.Ru = prep.deal_rows(ip, self.U, self.world)
+        slot_i, row_slot_i, self.Ri = prep.deal_rows(t_ip, self.I, self.world)
+        lo_u, lo_i = self.rank * self.Ru, self.rank * self.Ri
+        blk_u = prep.csr_block(ip, ix, slot_u[lo_u:lo_u + self.Ru], row_slot_i)
+        blk_i = prep.csr_block(t_ip, t_ix, slot_i[lo_i:lo_i + self.Ri], row_slot_u)
+        self.d_slot_u, self.d_slot_i = slot_u, slot_i
+        self.d_row_slot_u, self.d_row_slot_i = row_slot_u, row_slot_i
+        self.slot_u, self.slot_i = slot_u.cpu().numpy(), slot_i.cpu().numpy()
+        return blk_u, blk_i
 
     def _make_symmetric(self):
         """Move dW / dH into symmetric memory; returns {id(tensor): (handle, [peer base pointers])} or None."""
@@ -247,16 +298,22 @@ class AlsSession(object):
         return out
 
     def _upload(self, host, slots):
-        """Dense f64 [rows, K] -> device [len(slots), ld] in dealt order (phantom rows zero)."""
+        """Dense f64 [rows, K] ndarray (or a device tensor [rows, ld] of the session dtype) -> device
+        [len(slots), ld] in dealt order (phantom rows zero)."""
         import torch
-        dealt = np.zeros((slots.shape[0], host.shape[1]), np.float64)
-        dealt[slots >= 0] = host[slots[slots >= 0]]
-        return _lib.upload_factor(dealt, self.dtype, self.dev)
+        if isinstance(host, np.ndarray) and self.prep != "device":
+            dealt = np.zeros((slots.shape[0], host.shape[1]), np.float64)
+            dealt[slots >= 0] = host[slots[slots >= 0]]
+            return _lib.upload_factor(dealt, self.dtype, self.dev)
+        t = _lib.upload_factor(host, self.dtype, self.dev) if isinstance(host, np.ndarray) else host
+        d_slots = self.d_slot_u if slots is self.slot_u else self.d_slot_i
+        t = torch.cat([t, torch.zeros((1, t.shape[1]), dtype=t.dtype, device=t.device)])     # row for the phantoms
+        return t.index_select(0, torch.where(d_slots >= 0, d_slots, t.shape[0] - 1))
 
     # one half sweep: solve `rows_side` from the fixed side (wmf.pyx:136-174)
-    def _classes(self, blk):
+    def _classes(self, blk_indptr):
         """(rows solved with 16 warps, with 8, with 4): split of the block's rows (already heaviest first)."""
-        lengths = np.ascontiguousarray(np.diff(blk.indptr), np.int64)
+        lengths = np.ascontiguousarray(np.diff(blk_indptr.cpu().numpy()), np.int64)
         if self.force_width:                                   # tuning hook: one CTA width for every row
             n = int(lengths.shape[0])
             return {16: (n, 0, 0), 8: (0, n, 0), 4: (0, 0, n)}[self.force_width]
@@ -339,10 +396,8 @@ class AlsSession(object):
     def download(self, W, H):
         import torch
         with torch.cuda.device(self.dev):
-            for dev_m, slots, out in ((self.dW, self.slot_u, W), (self.dH, self.slot_i, H)):
-                dealt = np.empty((slots.shape[0], self.K), np.float64)
-                _lib.download_factor(dev_m, self.K, dealt)
-                out[slots[slots >= 0]] = dealt[slots >= 0]
+            for dev_m, row_slot, out in ((self.dW, self.d_row_slot_u, W), (self.dH, self.d_row_slot_i, H)):
+                _lib.download_factor(dev_m.index_select(0, row_slot), self.K, out)   # back to the caller's row order
 
     def dense_f64(self):
         """(W, H) as dense float64 DEVICE tensors in the caller's row order -- what the on-device evaluator scores."""

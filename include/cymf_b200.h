@@ -181,6 +181,35 @@ int cymf_glove_fit_host(const int32_t *central, const int32_t *context, const do
                         int64_t Vw, int64_t Vh, int32_t K, int32_t num_epochs,
                         double learning_rate, double x_max, double alpha, int mode, double *loss_out);
 
+/* ---- sparse-matrix preparation on the device -------------------------------------------
+ * What the reference does on the host per epoch / per fit: `X.T.tocsr()` twice per epoch (cymf/wmf.pyx:112) and the
+ * per-user positive sets (cymf/bpr.pyx:146-147; the sorted CSR row is the set here), plus the nnz-balanced row deal
+ * of the sharded ALS.  All results are exact and deterministic.  Every function takes a caller-provided device
+ * `workspace` of at least cymf_*_workspace_bytes(...) bytes. */
+int64_t cymf_scan_workspace_bytes(int64_t n);
+/* out[0..n] = exclusive prefix sums of in[0..n-1] (out[n] = total) */
+int cymf_exclusive_scan_u32_dev(const uint32_t *in, int64_t *out, int64_t n, void *workspace, void *stream);
+int64_t cymf_sort_workspace_bytes(int64_t n);
+/* stable LSD radix sort of (key, value) pairs by the low `key_bits` bits of the key, in place; values may be NULL */
+int cymf_sort_pairs_dev(uint32_t *keys, uint32_t *values, int64_t n, int32_t key_bits, void *workspace, void *stream);
+int64_t cymf_csr_transpose_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz);
+/* CSR of X^T (t_indptr int64[cols+1], t_indices int32[nnz], rows sorted) from the CSR of X: scipy's X.T.tocsr() */
+int cymf_csr_transpose_dev(const int64_t *indptr, const int32_t *indices, int64_t rows, int64_t cols, int64_t nnz,
+                           int64_t *t_indptr, int32_t *t_indices, void *workspace, void *stream);
+int64_t cymf_deal_workspace_bytes(int64_t rows);
+/* Heaviest-first round-robin deal of rows over `world` ranks: rows by decreasing degree (ties: ascending id), the
+ * q-th goes to rank q % world at position q / world.  slot_row[world*per_rank]: slot -> row id (-1 = phantom);
+ * row_slot[rows]: row id -> slot.  per_rank >= ceil(rows / world). */
+int cymf_deal_rows_dev(const int64_t *indptr, int64_t rows, int32_t world, int64_t per_rank,
+                       int64_t *slot_row, int64_t *row_slot, void *workspace, void *stream);
+int64_t cymf_csr_block_workspace_bytes(int64_t count);
+/* Row block in dealt order: block row q = source row slot_row[q] (empty when -1) with columns renamed through
+ * col_slot (NULL = keep).  Call once with blk_indices == NULL to get blk_indptr[count+1] (last entry = block nnz),
+ * then again with blk_indices allocated to copy the entries. */
+int cymf_csr_block_dev(const int64_t *indptr, const int32_t *indices, const int64_t *slot_row, int64_t count,
+                       const int64_t *col_slot, int64_t *blk_indptr, int32_t *blk_indices, void *workspace,
+                       void *stream);
+
 /* ---- WMF ALS (cymf/wmf.pyx:136-174, cymf/linalg.pyx:144-163) ------------------------------------------- */
 /* G = Y^T Y (+ weight_decay * I when add_weight_decay != 0), wmf.pyx:142-143.  Y is [n, ld] of `dtype`.
  * `workspace` needs cymf_gram_workspace_doubles(n, K) doubles (per-slab partials, reduced in a fixed order so
