@@ -80,6 +80,9 @@ SIGNATURES = {
     "cymf_chol_transforms_dev": (C.c_int, [_p, _i32, _i32, _f64, C.c_int, _p, _p, _p, _p, _p]),
     "cymf_rows_times_matrix_dev": (C.c_int, [_p, _p, _p, C.c_int, _i64, _i32, _p]),
     "cymf_rows_times_matrix_multi_dev": (C.c_int, [_p, C.POINTER(_p), _i32, _p, C.c_int, _i64, _i32, _p]),
+    "cymf_als_heavy_workspace_doubles": (_i64, [_i64, _i32, _i32]),
+    "cymf_als_heavy_rows_dev": (C.c_int, [_p, _p, _p, _i32, _p, _i32, _p, _p, _p, _f64, C.c_int, _i32, _i32, _f64, _p,
+                                          _i64, _p]),
     "cymf_als_row_classes": (C.c_int, [_p, _i64, C.c_int, _i32, _p, _p]),
     "cymf_als_half_host": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i32, _f64, _f64, C.c_int, _f64, _i32, _p]),
     "cymf_eval_candidates_host": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _i32, _u32, _p, _p, _i64]),

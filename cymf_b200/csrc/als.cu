@@ -483,6 +483,64 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
     }
 }
 
+// ---- heavy rows: direct solve ---------------------------------------------------------------------------------
+// A row with hundreds of thousands of entries keeps ONE CTA of the CG kernel busy for tens of milliseconds (its
+// item vectors are streamed ~7 times at a single SM's bandwidth) while the rest of the GPU has drained -- the tail of
+// every half sweep at C5, and the same at any GPU count.  For those rows the reference's own formulation is used
+// instead: the K x K matrix A = G + (w-1) sum y y^T (wmf.pyx:161-166) is accumulated ONCE, by many CTAs, on the
+// tensor cores (tc_gram_partial_kernel<GATHER>, 512 entries per slab), and solved directly (wmf.pyx:168) here:
+// one CTA per row sums the slab partials in slab order (deterministic), factors A = L D L^T in f64 in shared memory
+// and substitutes.  G == NULL means the identity (transformed coordinates).
+template <typename T>
+__global__ void __launch_bounds__(256) als_heavy_solve_kernel(const double *__restrict__ partial,
+                                                              const double *__restrict__ bsum,
+                                                              const int32_t *__restrict__ first_slab,
+                                                              const int32_t *__restrict__ order, T *__restrict__ X,
+                                                              const double *__restrict__ G, double add_diag, int K, int ld,
+                                                              double weight) {
+    extern __shared__ double sm[];
+    const int S = K + 1;                                    // padded stride: column walks spread over the banks
+    double *A = sm, *b = sm + (size_t)K * S;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int h = blockIdx.x, s0 = first_slab[h], s1 = first_slab[h + 1];
+    for (int t = tid; t < K * K; t += blockDim.x) {
+        double acc = 0.0;
+        for (int s = s0; s < s1; ++s) acc += partial[(size_t)s * K * K + t];
+        const int i = t / K, j = t - i * K;
+        const double g = G ? G[t] + (i == j ? add_diag : 0.0) : (i == j ? 1.0 : 0.0);
+        A[i * S + j] = g + (weight - 1.0) * acc;
+    }
+    for (int t = tid; t < K; t += blockDim.x) {
+        double acc = 0.0;
+        for (int s = s0; s < s1; ++s) acc += bsum[(size_t)s * ld + t];
+        b[t] = weight * acc;
+    }
+    __syncthreads();
+    for (int k = 0; k < K; ++k) {                           // L D L^T, column scaling deferred: one barrier per step
+        const double inv_d = 1.0 / A[k * S + k];
+        for (int i = k + 1 + ty; i < K; i += 8) {
+            const double lik = A[i * S + k] * inv_d;
+            for (int j = k + 1 + tx; j <= i; j += 32) A[i * S + j] -= lik * A[j * S + k];
+        }
+        __syncthreads();
+    }
+    for (int k = 0; k < K; ++k) {                           // forward: unit lower factor L_ik = A[i][k] / d_k
+        const double zk = b[k] / A[k * S + k];
+        __syncthreads();
+        for (int i = k + 1 + tid; i < K; i += blockDim.x) b[i] -= A[i * S + k] * zk;
+        __syncthreads();
+    }
+    for (int k = tid; k < K; k += blockDim.x) b[k] /= A[k * S + k];       // D^-1
+    __syncthreads();
+    for (int k = K - 1; k > 0; --k) {                       // backward: L^T x = y
+        const double xk = b[k];
+        for (int i = tid; i < k; i += blockDim.x) b[i] -= A[k * S + i] / A[i * S + i] * xk;
+        __syncthreads();
+    }
+    T *xr = X + (size_t)order[h] * ld;
+    for (int t = tid; t < ld; t += blockDim.x) xr[t] = t < K ? (T)b[t] : T(0);
+}
+
 template <typename T> static int gram_impl(const T *Y, int64_t n, int K, int ld, double wd, int add_wd, double *partial,
                                            int64_t partial_capacity, double *out64, T *outT, cudaStream_t st) {
     if constexpr (sizeof(T) == 4) {
@@ -847,6 +905,37 @@ extern "C" int cymf_als_cg_dev(const int64_t *indptr, const int32_t *indices, co
     }
     set_error("als: unknown dtype %d", dtype);
     return CYMF_EINVAL;
+}
+
+extern "C" int64_t cymf_als_heavy_workspace_doubles(int64_t n_slabs, int32_t K, int32_t ld) {
+    return n_slabs * ((int64_t)K * K + ld);
+}
+
+// Direct solve of the heavy rows order[0 .. n_heavy) of the block (see als_heavy_solve_kernel).  first_slab: device
+// int32[n_heavy + 1], first_slab[h + 1] - first_slab[h] = ceil(len_h / 512), first_slab[n_heavy] = n_slabs.
+// G64: dense [K, K] doubles (+ add_diag on the diagonal) or NULL for the identity (Y in transformed coordinates).
+// f32 factors with ld in {32, 64, 96, 128} only (tensor-core path); otherwise CYMF_EUNSUPPORTED.
+extern "C" int cymf_als_heavy_rows_dev(const int64_t *indptr, const int32_t *indices, const int32_t *order,
+                                       int32_t n_heavy, const int32_t *first_slab, int32_t n_slabs, void *X, const void *Y,
+                                       const double *G64, double add_diag, int dtype, int32_t K, int32_t ld, double weight,
+                                       double *workspace, int64_t workspace_doubles, void *stream) {
+    CYMF_REQUIRE(indptr && indices && order && first_slab && X && Y && workspace, "null pointer");
+    CYMF_REQUIRE(n_heavy >= 0 && n_slabs >= n_heavy && K > 0 && ld >= K, "bad shape");
+    if (!(tc_shape_ok(dtype, ld) && tc_enabled())) {
+        set_error("als heavy rows: needs f32 factors with ld in {32, 64, 96, 128} and tcgen05 enabled");
+        return CYMF_EUNSUPPORTED;
+    }
+    if (n_heavy == 0) return 0;
+    CYMF_REQUIRE(workspace_doubles >= cymf_als_heavy_workspace_doubles(n_slabs, K, ld), "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    double *partial = workspace, *bsum = workspace + (size_t)n_slabs * K * K;
+    CYMF_TRY(tc_gram_gather((const float *)Y, indptr, indices, order, first_slab, n_heavy, n_slabs, K, ld, partial, bsum, st));
+    const size_t smem = sizeof(double) * ((size_t)K * (K + 1) + K);
+    CYMF_CUDA(cudaFuncSetAttribute(als_heavy_solve_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    als_heavy_solve_kernel<float><<<(unsigned)n_heavy, 256, smem, st>>>(partial, bsum, first_slab, order, (float *)X, G64,
+                                                                      add_diag, K, ld, weight);
+    CYMF_LAUNCHED();
+    return 0;
 }
 
 // Rows sorted by decreasing length split into three classes by how many item vectors fit the staging area of a

@@ -39,6 +39,9 @@ int tc_rows_times_matrix(const float *in, float *const *outs, int n_outs, const 
                          cudaStream_t st);
 int64_t tc_gram_slabs(int64_t n);
 int tc_gram_partial(const float *Y, int64_t n, int K, int ld, double *partial, cudaStream_t st);
+int tc_gram_gather(const float *Y, const int64_t *indptr, const int32_t *indices, const int32_t *order,
+                   const int32_t *first_slab, int n_heavy, int n_slabs, int K, int ld, double *partial, double *bsum,
+                   cudaStream_t st);
 bool tc_enabled();      // false when the environment sets CYMF_NO_TCGEN05=1 (A/B comparisons in tests and tools)
 
 #define CYMF_TRY(expr)             \

@@ -7,7 +7,9 @@
 //       it is given -- with the peers' replicas of the factor matrix as destinations this one kernel is the GEMM and
 //       the all-gather over NVLink peer memory.
 //   tc_gram_partial_kernel      : per-slab partial of G = Y^T Y (cymf/wmf.pyx:142) with the same machinery; slabs are
-//       summed in f64 in a fixed order by gram_finish_kernel (als.cu).
+//       summed in f64 in a fixed order by gram_finish_kernel (als.cu).  Its GATHER form builds, slab by slab, the
+//       per-row matrix sum_{c in row} y_c y_c^T (wmf.pyx:161-166) of the few very long rows of a half sweep, which
+//       are then solved directly (als_heavy_solve_kernel) instead of being streamed ~7 times by one CTA.
 //
 // Precision: kind::tf32 keeps 10 mantissa bits per operand, far too few for the 1e-4 parity bar, so every operand
 // is split as a = hi + lo (hi = a with the low 13 mantissa bits cleared, lo = a - hi, both exactly representable) and
@@ -19,6 +21,7 @@ namespace cymf {
 namespace tc {
 
 constexpr int TILE_M = 128;       // rows of D (TMEM lanes)
+constexpr int TC_GRAM_SLAB = 512; // rows of Y per Gram partial
 constexpr int CHUNK_K = 32;       // reduction elements staged per step: 8 x 16-byte chunks, 4 MMA k-slices of 8
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -208,10 +211,24 @@ __global__ void __launch_bounds__(128) tc_rows_times_matrix_kernel(const float *
 // partial[slab] = Y[slab rows]^T Y[slab rows]  (dense [K, K] doubles, like gram_partial_kernel).
 // Each 32-row chunk is multiplied on the tensor cores into a fresh TMEM accumulator (12 MMAs), read back and added
 // into an f64 copy of the slab's result in shared memory, so the truncating f32 accumulation never runs long chains.
-constexpr int TC_GRAM_SLAB = 512;
+// GATHER = false: slab b = rows [512 b, 512 b + 512) of Y.
+// GATHER = true : slab s belongs to heavy row h (first_slab[h] <= s < first_slab[h + 1]) of a CSR; its operand rows are
+//                 Y[indices[lo + t]] for the row's entries t in [512 (s - first_slab[h]), ...): the partial of
+//                 sum_{c in row} y_c y_c^T that the reference accumulates entry by entry (cymf/wmf.pyx:161-166);
+//                 bsum[s][m] = sum of the slab's y_c[m] (wmf.pyx:163).
+struct GatherPlan {
+    const int64_t *indptr;
+    const int32_t *indices;
+    const int32_t *order;          // heavy row h = CSR row order[h]
+    const int32_t *first_slab;     // [n_heavy + 1]
+    int32_t n_heavy;
+    double *bsum;                  // [n_slabs][ld]
+};
 
+template <bool GATHER>
 __global__ void __launch_bounds__(128) tc_gram_partial_kernel(const float *__restrict__ Y, int64_t n, int K, int ld,
-                                                              double *__restrict__ partial, uint32_t tmem_cols) {
+                                                              double *__restrict__ partial, uint32_t tmem_cols,
+                                                              const GatherPlan plan) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *t_hi = reinterpret_cast<float *>(smem_raw);            // [TILE_M x 32]: operand rows = columns of Y (zero past ld)
     float *t_lo = t_hi + TILE_M * CHUNK_K;
@@ -228,17 +245,35 @@ __global__ void __launch_bounds__(128) tc_gram_partial_kernel(const float *__res
     const uint32_t d_tmem = tmem_slot;
     const uint32_t idesc = idesc_tf32(ld);
     const int groups = TILE_M / 8;
-    const int64_t r0 = (int64_t)blockIdx.x * TC_GRAM_SLAB;
-    const int64_t r1 = r0 + TC_GRAM_SLAB < n ? r0 + TC_GRAM_SLAB : n;
+    int64_t r0, r1;
+    const int32_t *gidx = nullptr;
+    if (GATHER) {
+        int lo = 0, hi = plan.n_heavy;                            // last h with first_slab[h] <= blockIdx.x
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (plan.first_slab[mid] <= (int)blockIdx.x) lo = mid; else hi = mid; }
+        const int32_t row = plan.order[lo];
+        const int64_t beg = plan.indptr[row], end = plan.indptr[row + 1];
+        r0 = beg + (int64_t)((int)blockIdx.x - plan.first_slab[lo]) * TC_GRAM_SLAB;
+        r1 = r0 + TC_GRAM_SLAB < end ? r0 + TC_GRAM_SLAB : end;
+        gidx = plan.indices;
+    } else {
+        r0 = (int64_t)blockIdx.x * TC_GRAM_SLAB;
+        r1 = r0 + TC_GRAM_SLAB < n ? r0 + TC_GRAM_SLAB : n;
+    }
+    double colsum = 0.0;
     uint32_t phase = 0;
     for (int64_t base = r0; base < r1; base += CHUNK_K) {
-        // operand element (m, k) = Y[base + k][m]; thread m (column of Y), zero rows for m >= ld or past the slab
+        // operand element (m, k) = Y[row(base + k)][m]; thread m (column of Y), zero rows for m >= ld or past the slab
         const float *src = Y + (size_t)base * ld + tid;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             float e[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) e[t] = (tid < ld && base + 4 * q + t < r1) ? __ldg(src + (size_t)(4 * q + t) * ld) : 0.f;
+            for (int t = 0; t < 4; ++t) {
+                const bool ok = tid < ld && base + 4 * q + t < r1;
+                if (GATHER) e[t] = ok ? __ldg(Y + (size_t)__ldg(gidx + base + 4 * q + t) * ld + tid) : 0.f;
+                else e[t] = ok ? __ldg(src + (size_t)(4 * q + t) * ld) : 0.f;
+            }
+            if (GATHER) colsum += ((double)e[0] + (double)e[1]) + ((double)e[2] + (double)e[3]);
             const float4 v = make_float4(e[0], e[1], e[2], e[3]);
             const float4 h = tf32_hi(v);
             const int o = tile_off(tid, q, groups);
@@ -269,6 +304,7 @@ __global__ void __launch_bounds__(128) tc_gram_partial_kernel(const float *__res
     double *out = partial + (size_t)blockIdx.x * K * K;
     if (tid < K)
         for (int c = 0; c < K; ++c) out[(size_t)tid * K + c] = acc[c * TILE_M + tid];
+    if (GATHER && tid < ld) plan.bsum[(size_t)blockIdx.x * ld + tid] = colsum;
     __syncthreads();
     if (warp == 0) tmem_dealloc(d_tmem, tmem_cols);
 }
@@ -310,8 +346,22 @@ int tc_gram_partial(const float *Y, int64_t n, int K, int ld, double *partial, c
     const int64_t slabs = tc_gram_slabs(n);
     if (slabs == 0) return 0;
     const size_t smem = sizeof(float) * (size_t)(2 * tc::TILE_M * tc::CHUNK_K) + sizeof(double) * (size_t)ld * tc::TILE_M;
-    CYMF_CUDA(cudaFuncSetAttribute(tc::tc_gram_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc::tc_gram_partial_kernel<<<(unsigned)slabs, 128, smem, st>>>(Y, n, K, ld, partial, tc::tmem_columns(ld, 1));
+    CYMF_CUDA(cudaFuncSetAttribute(tc::tc_gram_partial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc::tc_gram_partial_kernel<false><<<(unsigned)slabs, 128, smem, st>>>(Y, n, K, ld, partial, tc::tmem_columns(ld, 1),
+                                                                         tc::GatherPlan{});
+    CYMF_LAUNCHED();
+    return 0;
+}
+
+// per-slab partials of sum_{c in row} y_c y_c^T (+ column sums) for the heavy rows order[0 .. n_heavy) of a CSR
+int tc_gram_gather(const float *Y, const int64_t *indptr, const int32_t *indices, const int32_t *order,
+                   const int32_t *first_slab, int n_heavy, int n_slabs, int K, int ld, double *partial, double *bsum,
+                   cudaStream_t st) {
+    if (n_slabs <= 0) return 0;
+    const size_t smem = sizeof(float) * (size_t)(2 * tc::TILE_M * tc::CHUNK_K) + sizeof(double) * (size_t)ld * tc::TILE_M;
+    CYMF_CUDA(cudaFuncSetAttribute(tc::tc_gram_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc::GatherPlan plan{indptr, indices, order, first_slab, n_heavy, bsum};
+    tc::tc_gram_partial_kernel<true><<<(unsigned)n_slabs, 128, smem, st>>>(Y, 0, K, ld, partial, tc::tmem_columns(ld, 1), plan);
     CYMF_LAUNCHED();
     return 0;
 }

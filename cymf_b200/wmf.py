@@ -16,6 +16,7 @@ rank holds a full replica of both factor matrices, solves its own block, then th
 K x K Gram partials of the freshly solved blocks are all-reduced.  world_size == 1 runs the same code.
 """
 import ctypes as C
+import os
 
 import numpy as np
 from scipy import sparse
@@ -38,7 +39,7 @@ class WMF(object):
 
     def __init__(self, num_components=20, weight_decay=0.01, weight=10.0, *, dtype="float32", cg_tol=None,
                  cg_max_iter=None, device=None, distributed="auto", peer_gather=True, solver="transformed",
-                 prep="device"):
+                 prep="device", heavy_min=4096):
         self.num_components = int(num_components)
         self.weight_decay = float(weight_decay)
         self.weight = float(weight)
@@ -58,6 +59,7 @@ class WMF(object):
         if prep not in ("device", "host"):
             raise ValueError("prep must be 'device' or 'host'")
         self.prep = prep                 # where X^T, the row deal and the relabelled blocks are built
+        self.heavy_min = int(heavy_min)  # rows with at least this many entries are solved directly (0 = never)
         self.cg_iterations_ = 0          # CG iterations summed over rows, last fit
         self.cg_unconverged_ = 0         # rows that stopped at cg_max_iter, last fit
 
@@ -104,7 +106,8 @@ class WMF(object):
         tol, iters = self._tolerances()
         sess = AlsSession(X, self.W, self.H, self.weight_decay, self.weight, dtype=self.dtype, cg_tol=tol,
                           cg_max_iter=iters, device=self.device, distributed=self.distributed,
-                          peer_gather=self.peer_gather, solver=self.solver, prep=self.prep)
+                          peer_gather=self.peer_gather, solver=self.solver, prep=self.prep,
+                          heavy_min=self.heavy_min)
         # how solved blocks reach the other ranks: "single" | "peer-store" (fused into the GEMM epilogue) | "nccl"
         self.gather_mode_ = "peer-store" if sess.peer else ("nccl" if sess.dist else "single")
         run_epochs(self, sess, num_epochs, sess.epoch, verbose, ncols=100)
@@ -156,8 +159,9 @@ class AlsSession(object):
 
     def __init__(self, X, W, H, weight_decay, weight, *, K=None, dtype="float32", cg_tol=1e-6, cg_max_iter=128, device=None,
                  distributed="auto", stage_rows=0, force_width=0, solver="transformed", peer_gather=True,
-                 prep="device"):
+                 prep="device", overlap_classes=True, heavy_min=4096):
         torch = _lib.require_cuda()
+        self.heavy_min = int(heavy_min)
         self.peer_error = None
         self._unperm = {}
         self.force_width = int(force_width)
@@ -178,6 +182,7 @@ class AlsSession(object):
         self.wd, self.weight = float(weight_decay), float(weight)
         self.cg_tol, self.cg_max_iter, self.stage_rows = float(cg_tol), int(cg_max_iter), int(stage_rows)
         self.prep = prep
+        self._side, self.overlap_classes = None, bool(overlap_classes)
         with torch.cuda.device(dev):
             if prep == "device":
                 blk_u, blk_i = self._prepare_on_device(X)
@@ -185,8 +190,11 @@ class AlsSession(object):
                 blk_u, blk_i = self._prepare_on_host(X)
             self.csr_u, self.csr_i = blk_u, blk_i
             self.block_nnz = (int(blk_u[1].numel()), int(blk_i[1].numel()))
-            self.classes_u = self._classes(blk_u[0])
-            self.classes_i = self._classes(blk_i[0])
+            self.classes_u, self.heavy_u = self._classes(blk_u[0])
+            self.classes_i, self.heavy_i = self._classes(blk_i[0])
+            n_slabs = max(int(h[1][-1]) if h else 0 for h in (self.heavy_u, self.heavy_i))
+            self.ws_heavy = torch.empty(max(1, int(self._L.cymf_als_heavy_workspace_doubles(n_slabs, K, ld))),
+                                        dtype=torch.float64, device=dev)
             U, I, Up, Ip = self.U, self.I, self.slot_u.shape[0], self.slot_i.shape[0]
             self.order_u = torch.arange(self.Ru, dtype=torch.int32, device=dev)
             self.order_i = torch.arange(self.Ri, dtype=torch.int32, device=dev)
@@ -205,7 +213,7 @@ class AlsSession(object):
             self.Ginv = torch.empty(ld * ld, dtype=tdt, device=dev)
             self.By, self.Bfwd, self.Bbwd = (torch.empty(ld * ld, dtype=tdt, device=dev) for _ in range(3))
             self.Yt = torch.empty((max(Up, Ip), ld), dtype=tdt, device=dev)     # fixed side in transformed coordinates
-            self.queue = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.queue = torch.zeros(4, dtype=torch.int32, device=dev)     # one work-queue head per row class
             self.d_stats = torch.zeros(2, dtype=torch.int64, device=dev)
         self.epochs_done = 0
         self.h2d_bytes = self._nbytes(W) + self._nbytes(H) + 8 * (self.Ru + self.Ri + 2) + 4 * sum(self.block_nnz)
@@ -312,17 +320,39 @@ class AlsSession(object):
 
     # one half sweep: solve `rows_side` from the fixed side (wmf.pyx:136-174)
     def _classes(self, blk_indptr):
-        """(rows solved with 16 warps, with 8, with 4): split of the block's rows (already heaviest first)."""
+        """Split of the block's rows (already heaviest first): ((rows solved by CG with 16 warps, with 8, with 4),
+        heavy) where heavy = (n_heavy, first_slab device int32[n_heavy+1]) are the leading rows of at least
+        `heavy_min` entries that are solved directly (cymf_als_heavy_rows_dev), or None."""
+        import torch
         lengths = np.ascontiguousarray(np.diff(blk_indptr.cpu().numpy()), np.int64)
+        n = int(lengths.shape[0])
         if self.force_width:                                   # tuning hook: one CTA width for every row
-            n = int(lengths.shape[0])
-            return {16: (n, 0, 0), 8: (0, n, 0), 4: (0, 0, n)}[self.force_width]
+            return {16: (n, 0, 0), 8: (0, n, 0), 4: (0, 0, n)}[self.force_width], None
         n16, n8 = C.c_int64(0), C.c_int64(0)
-        _lib.check(self._L.cymf_als_row_classes(lengths.ctypes.data_as(C.c_void_p), lengths.shape[0], self.dtype,
+        _lib.check(self._L.cymf_als_row_classes(lengths.ctypes.data_as(C.c_void_p), n, self.dtype,
                                                 self.ld, C.byref(n16), C.byref(n8)))
-        return int(n16.value), int(n8.value), int(lengths.shape[0] - n16.value - n8.value)
+        b16, b8 = int(n16.value), int(n16.value + n8.value)
+        heavy, nh = None, 0
+        if (self.heavy_min > 0 and self.solver == "transformed" and self.dtype == _lib.F32 and self.ld % 32 == 0
+                and self.ld <= 128 and os.environ.get("CYMF_NO_TCGEN05") != "1"):
+            # Machine time is about the same either way (CG: ~0.05-0.11 us x n on ONE SM; direct: n / 512 slabs of
+            # ~64 us spread over all SMs + a 0.35 ms solve), so the direct path only pays for rows that would stick
+            # out as a tail: row time >= ~half of the block's time (~0.45 ns per entry)  <=>  n >= block nnz / 256.
+            # Measured: ml-20m on one GPU has no such row (19.4 ms/epoch either way, 22.2 ms with a floor of 4096);
+            # sharded over 8 GPUs the same rows are 8x larger relative to their block and do qualify.
+            floor = max(self.heavy_min, int(lengths.sum()) // 256)
+            while True:                                        # keep the slab workspace under 8 GB
+                nh = int((lengths >= floor).sum())             # a prefix: lengths are sorted in decreasing order
+                slabs = int(((lengths[:nh] + 511) // 512).sum())
+                if slabs * (self.K * self.K + self.ld) * 8 <= 8e9:
+                    break
+                floor *= 2
+            if nh:
+                first = np.concatenate([[0], np.cumsum((lengths[:nh] + 511) // 512)]).astype(np.int32)
+                heavy = (nh, first, torch.from_numpy(first).to(self.dev))
+        return (max(b16 - nh, 0), max(b8 - max(nh, b16), 0), n - max(nh, b8)), heavy
 
-    def _half(self, X_full, R, csr, order, Y_full, Ry, classes):
+    def _half(self, X_full, R, csr, order, Y_full, Ry, classes, heavy):
         import torch
         L, K, ld = self._L, self.K, self.ld
         stream = _lib.stream_ptr()
@@ -355,16 +385,50 @@ class AlsSession(object):
         elif self.solver == "pcg":                               # G^-1 as CG preconditioner (f64 Gauss-Jordan, one CTA)
             _lib.check(L.cymf_spd_inverse_dev(_lib.ptr(self.g64), K, ld, add_diag, self.dtype, _lib.ptr(self.Ginv), stream))
             ginv = self.Ginv
-        # rows of the block are sorted heaviest first: 16 warps per row for the longest, then 8, then 4
-        start = 0
-        for width, count in zip((16, 8, 4), classes):
+        # rows of the block are sorted heaviest first: 16 warps per row for the longest, then 8, then 4.  The three
+        # class kernels are independent (disjoint rows, own work queues): the two heavy classes go to side streams
+        # so that their tails -- a handful of very long rows -- drain underneath the bulk of the short rows.
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = [torch.cuda.Stream(device=self.dev) for _ in range(3)]
+        fork = torch.cuda.Event()
+        fork.record(main)
+        start, joins = 0, []
+        if heavy:
+            # the few very long rows: K x K matrix built once by many CTAs on the tensor cores, solved directly
+            nh, first_host, first_dev = heavy
+            st = self._side[2] if self.overlap_classes else main
+            if st is not main:
+                st.wait_event(fork)
+            with torch.cuda.stream(st):
+                _lib.check(L.cymf_als_heavy_rows_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order), nh,
+                                                     _lib.ptr(first_dev), int(first_host[-1]), _lib.ptr(x_blk),
+                                                     _lib.ptr(y_used), None, 0.0, self.dtype, K, ld, self.weight,
+                                                     _lib.ptr(self.ws_heavy), self.ws_heavy.numel(), _lib.stream_ptr()))
+                if st is not main:
+                    done = torch.cuda.Event()
+                    done.record(st)
+                    joins.append(done)
+            start = nh
+        for c, (width, count) in enumerate(zip((16, 8, 4), classes)):
             if count:
-                _lib.check(L.cymf_als_cg_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order[start:]), count,
-                                             _lib.ptr(x_blk), _lib.ptr(y_used), _lib.ptr(g), _lib.ptr(ginv),
-                                             self.dtype, K, ld,
-                                             self.weight, self.cg_tol, self.cg_max_iter, width, self.stage_rows,
-                                             _lib.ptr(self.queue), _lib.ptr(self.d_stats), stream))
+                st = self._side[c] if (c < 2 and self.overlap_classes) else main
+                if st is not main:
+                    st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    _lib.check(L.cymf_als_cg_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order[start:]), count,
+                                                 _lib.ptr(x_blk), _lib.ptr(y_used), _lib.ptr(g), _lib.ptr(ginv),
+                                                 self.dtype, K, ld,
+                                                 self.weight, self.cg_tol, self.cg_max_iter, width, self.stage_rows,
+                                                 _lib.ptr(self.queue[c:]), _lib.ptr(self.d_stats), _lib.stream_ptr()))
+                    if st is not main:
+                        done = torch.cuda.Event()
+                        done.record(st)
+                        joins.append(done)
             start += count
+        for done in joins:
+            main.wait_event(done)
+        stream = _lib.stream_ptr()
         if self.solver == "transformed" and self.peer is not None:
             # back-transform + all-gather in one kernel: every solved row is stored into all replicas over NVLink
             hdl, ptrs = self.peer[X_full.data_ptr()]
@@ -381,10 +445,10 @@ class AlsSession(object):
             self.dist.all_gather_into_tensor(X_full, x_blk)
 
     def user_half(self):
-        self._half(self.dW, self.Ru, self.csr_u, self.order_u, self.dH, self.Ri, self.classes_u)
+        self._half(self.dW, self.Ru, self.csr_u, self.order_u, self.dH, self.Ri, self.classes_u, self.heavy_u)
 
     def item_half(self):
-        self._half(self.dH, self.Ri, self.csr_i, self.order_i, self.dW, self.Ru, self.classes_i)
+        self._half(self.dH, self.Ri, self.csr_i, self.order_i, self.dW, self.Ru, self.classes_i, self.heavy_i)
 
     def epoch(self):
         import torch

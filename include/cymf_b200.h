@@ -264,6 +264,18 @@ int cymf_rows_times_matrix_dev(const void *in, void *out, const void *B, int dty
 int cymf_rows_times_matrix_multi_dev(const void *in, void *const *outs, int32_t n_outs, const void *B, int dtype,
                                      int64_t rows, int32_t ld, void *stream);
 
+/* Direct solve of the block's heaviest rows order[0 .. n_heavy) (rows are sorted heaviest first): the K x K matrix
+ * G + (weight-1) sum_{c in row} y_c y_c^T the reference materialises per row (cymf/wmf.pyx:161-166) is accumulated
+ * once on the tensor cores, 512 entries per CTA, and solved in f64 (wmf.pyx:168) -- instead of one CTA streaming a
+ * 700 k-entry row ~7 times while the GPU idles.  first_slab: device int32[n_heavy+1], slab counts ceil(len/512)
+ * prefix-summed.  G64 dense [K,K] doubles (+ add_diag on the diagonal), or NULL = identity (Y in the transformed
+ * coordinates of cymf_chol_transforms_dev).  f32, ld in {32,64,96,128}; otherwise CYMF_EUNSUPPORTED. */
+int64_t cymf_als_heavy_workspace_doubles(int64_t n_slabs, int32_t K, int32_t ld);
+int cymf_als_heavy_rows_dev(const int64_t *indptr, const int32_t *indices, const int32_t *order, int32_t n_heavy,
+                            const int32_t *first_slab, int32_t n_slabs, void *X, const void *Y, const double *G64,
+                            double add_diag, int dtype, int32_t K, int32_t ld, double weight, double *workspace,
+                            int64_t workspace_doubles, void *stream);
+
 /* warps_per_row of cymf_als_cg_dev is 4, 8 or 16 (CTA width per row; each warp brings 8 KB of shared-memory
  * staging for the row's item vectors).  Given the row lengths in `order` (decreasing), this returns how many
  * leading rows should be solved with 16 warps and how many following ones with 8; the rest take 4. */

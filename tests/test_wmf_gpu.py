@@ -103,3 +103,23 @@ def test_evaluator_hook_and_early_stopping():
         cymf.WMF().fit(train, early_stopping=True)
     with pytest.raises(ValueError):
         cymf.WMF().fit(None)
+
+
+@pytest.mark.parametrize("K", [32, 64, 128])
+def test_heavy_rows_direct_solve(oracle, K):
+    """Rows of >= heavy_min entries take the direct path (gathered tcgen05 Gram per 512-entry slab + f64 LDL^T solve,
+    cymf_als_heavy_rows_dev) instead of CG: same factors as the reference's dgesv solves, and as the CG path."""
+    import cymf_b200 as cymf
+    X = cymf.synth.synth_implicit(900, 700, 60000, seed=12).tolil()
+    X[3, :] = 1                                               # a row with every item: 700 entries = 2 slabs
+    X[:, 5] = 1                                               # and a column with every user: 900 entries
+    X = X.tocsr()
+    Wo, Ho = oracle.wmf_fit(X, K, 0.01, 10.0, 2)
+    out = {}
+    for heavy_min in (0, 100):
+        m = cymf.WMF(K, 0.01, 10.0, heavy_min=heavy_min)
+        m.fit(X, 2, 1, verbose=False)
+        out[heavy_min] = (m.W.copy(), m.H.copy())
+        for got, want in ((m.W, Wo), (m.H, Ho)):
+            assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max(), (heavy_min, np.abs(got - want).max())
+    assert np.abs(out[0][0] - out[100][0]).max() <= 2e-5 * np.abs(Wo).max()
