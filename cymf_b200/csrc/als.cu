@@ -382,31 +382,51 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
         }                                                                                          \
         out = o_;
 
-        // stage the row's item vectors and accumulate b = w * sum y_i (wmf.pyx:163)
+        // Fused first pass over the row: stage its item vectors, accumulate b = w * sum y_i (wmf.pyx:163) AND the
+        // (w-1) sum y_i (y_i . x0) term of A x0 for the warm start x0, so that r0 = b - A x0 costs no second pass
+        // (one of the ~7 passes a row takes).  Groups of four items, the next group's gathers already in flight.
+        if (own) p_s[tid] = xr[tid];                                            // warm start
+        __syncthreads();
+        T acc[VW];
         {
-            T bacc[VW];
+            T bacc[VW], ps[VW], c0[VW], c1[VW], c2[VW], c3[VW];
 #pragma unroll
-            for (int e = 0; e < VW; ++e) bacc[e] = T(0);
-            if (lane_on) {
-                int i = warp;
-                for (; i + NW < nnz; i += 2 * NW) {                            // two gathers in flight
-                    T v0[VW], v1[VW];
-                    ldg_vec<VW>(Yq + (size_t)__ldg(idx + i) * ld, v0);
-                    ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + NW) * ld, v1);
-#pragma unroll
-                    for (int e = 0; e < VW; ++e) bacc[e] += v0[e] + v1[e];
-                    if (i < ns) st_vec<VW>(Ys + i * ld + kq, v0);
-                    if (i + NW < ns) st_vec<VW>(Ys + (i + NW) * ld + kq, v1);
-                }
-                if (i < nnz) {
-                    T v0[VW];
-                    ldg_vec<VW>(Yq + (size_t)__ldg(idx + i) * ld, v0);
-#pragma unroll
-                    for (int e = 0; e < VW; ++e) bacc[e] += v0[e];
-                    if (i < ns) st_vec<VW>(Ys + i * ld + kq, v0);
-                }
-                st_vec<VW>(part + warp * CG_VEC + kq, bacc);
+            for (int e = 0; e < VW; ++e) { bacc[e] = acc[e] = ps[e] = T(0); c0[e] = c1[e] = c2[e] = c3[e] = T(0); }
+            if (lane_on) ld_vec<VW>(p_s + kq, ps);
+#define CYMF_GATHER4(at, v0, v1, v2, v3)                                                           \
+            if (lane_on) {                                                                         \
+                if ((at) < nnz) ldg_vec<VW>(Yq + (size_t)__ldg(idx + (at)) * ld, v0);              \
+                if ((at) + NW < nnz) ldg_vec<VW>(Yq + (size_t)__ldg(idx + (at) + NW) * ld, v1);    \
+                if ((at) + 2 * NW < nnz) ldg_vec<VW>(Yq + (size_t)__ldg(idx + (at) + 2 * NW) * ld, v2); \
+                if ((at) + 3 * NW < nnz) ldg_vec<VW>(Yq + (size_t)__ldg(idx + (at) + 3 * NW) * ld, v3); \
             }
+            CYMF_GATHER4(warp, c0, c1, c2, c3)
+            for (int i = warp; i < nnz; i += 4 * NW) {
+                T n0[VW], n1[VW], n2[VW], n3[VW];
+#pragma unroll
+                for (int e = 0; e < VW; ++e) n0[e] = n1[e] = n2[e] = n3[e] = T(0);
+                CYMF_GATHER4(i + 4 * NW, n0, n1, n2, n3)
+                if (lane_on) {
+                    if (i < ns) st_vec<VW>(Ys + i * ld + kq, c0);
+                    if (i + NW < ns) st_vec<VW>(Ys + (i + NW) * ld + kq, c1);
+                    if (i + 2 * NW < ns) st_vec<VW>(Ys + (i + 2 * NW) * ld + kq, c2);
+                    if (i + 3 * NW < ns) st_vec<VW>(Ys + (i + 3 * NW) * ld + kq, c3);
+                }
+                T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
+#pragma unroll
+                for (int e = 0; e < VW; ++e) {
+                    bacc[e] += (c0[e] + c1[e]) + (c2[e] + c3[e]);
+                    d0 += c0[e] * ps[e]; d1 += c1[e] * ps[e]; d2 += c2[e] * ps[e]; d3 += c3[e] * ps[e];
+                }
+                warp_allsum4(d0, d1, d2, d3, lane);
+#pragma unroll
+                for (int e = 0; e < VW; ++e) {
+                    acc[e] += (d0 * c0[e] + d1 * c1[e]) + (d2 * c2[e] + d3 * c3[e]);
+                    c0[e] = n0[e]; c1[e] = n1[e]; c2[e] = n2[e]; c3[e] = n3[e];
+                }
+            }
+#undef CYMF_GATHER4
+            if (lane_on) st_vec<VW>(part + warp * CG_VEC + kq, bacc);
         }
         __syncthreads();
         T b = T(0), x = T(0);
@@ -414,16 +434,17 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
 #pragma unroll
             for (int w = 0; w < NW; ++w) b += part[w * CG_VEC + tid];
             b *= a.weight;
-            x = xr[tid];                                                        // warm start
-            p_s[tid] = x;
+            x = p_s[tid];
         }
         T bb;
-        CYMF_BLOCK_SUM(bb, b * b);                                              // barrier: p_s, Ys and part are settled
+        CYMF_BLOCK_SUM(bb, b * b);                                              // barrier: Ys is settled, part has been read
         unsigned iters = 0;
         bool stalled = false;
         if (bb > T(0)) {
             T Ax;
-            CYMF_APPLY(Ax);
+#pragma unroll
+            for (int e = 0; e < VW; ++e) acc[e] *= wm1;
+            CYMF_APPLY_TAIL(Ax)                                                 // + G x0 (or + x0), combine the warps
             T res = b - Ax;                                                     // r0 = b - A x0
             T rs, rz;
             T z = res;

@@ -30,7 +30,8 @@ for r in rows[2:]:
             u = units[hdr.index(k)]; v = float(d[k].replace(",", ""))
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
         tr = b("dram__bytes_read.sum") + b("dram__bytes_write.sum")
-        out.append(f"  -> duration {t*1e3:.3f} ms, DRAM traffic {tr/1e9:.3f} GB ({tr/t/1e9:.0f} GB/s), L2 traffic {b('lts__t_bytes.sum')/1e9:.3f} GB ({b('lts__t_bytes.sum')/t/1e9:.0f} GB/s)")
+        l2 = f", L2 traffic {b('lts__t_bytes.sum')/1e9:.3f} GB ({b('lts__t_bytes.sum')/t/1e9:.0f} GB/s)" if "lts__t_bytes.sum" in hdr else ""
+        out.append(f"  -> duration {t*1e3:.3f} ms, DRAM traffic {tr/1e9:.3f} GB ({tr/t/1e9:.0f} GB/s){l2}")
     except Exception as e:
         out.append(f"  (derived failed: {e})")
 text = "\n".join(out)
