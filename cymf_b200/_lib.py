@@ -71,6 +71,8 @@ SIGNATURES = {
     "cymf_deal_rows_dev": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _p]),
     "cymf_csr_block_workspace_bytes": (_i64, [_i64]),
     "cymf_csr_block_dev": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _p, _p]),
+    "cymf_cooc_workspace_bytes": (_i64, [_i64, _i32]),
+    "cymf_cooc_count_dev": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _i64, _p, _p, _p]),
     "cymf_gram_workspace_doubles": (_i64, [_i64, _i32]),
     "cymf_gram_dev": (C.c_int, [_p, C.c_int, _i64, _i32, _i32, _f64, C.c_int, _p, _i64, _p, _p, _p]),
     "cymf_gram_finalize_dev": (C.c_int, [_p, C.c_int, _i32, _i32, _f64, _p, _p]),

@@ -398,3 +398,117 @@ extern "C" int cymf_csr_block_dev(const int64_t *indptr, const int32_t *indices,
     CYMF_LAUNCHED();
     return 0;
 }
+
+// ---- co-occurrence counting: the loop of read_text (cymf/glove.pyx:218-221) ----------------------------------------
+//     for every kept token j of a line and every earlier kept token k of the same line with j - k <= window:
+//         M[x_j, x_k] += 1.0 / (j - k)                        (an unordered_map<long, double> in the reference)
+// Sort-based and exact: pair slot p = j * window + (window - d), d = j - k, enumerates the reference's updates in ITS
+// order (j ascending, k ascending); two stable radix sorts (by column, then by row) group the slots of a cell while
+// keeping that order, and each cell is summed sequentially in f64 -- the same additions in the same order, so the
+// counts are bit-identical to the reference's.  Output triplets are sorted by (row, col).
+namespace cymf {
+
+struct CoocView {
+    const int32_t *tokens, *pos;
+    int64_t n_pairs;
+    int32_t window, vocab;
+    __device__ __forceinline__ bool decode(uint32_t p, int32_t *row, int32_t *col, int32_t *dist) const {
+        const int64_t j = p / (uint32_t)window;
+        const int32_t d = window - (int32_t)(p % (uint32_t)window);
+        *dist = d;
+        if (d > pos[j]) return false;                       // would reach before the start of the line
+        *row = tokens[j];
+        *col = tokens[j - d];
+        return true;
+    }
+};
+
+__global__ void cooc_col_keys_kernel(const CoocView v, uint32_t *__restrict__ keys, uint32_t *__restrict__ ids) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < v.n_pairs; p += (int64_t)gridDim.x * blockDim.x) {
+        int32_t r, c, d;
+        keys[p] = v.decode((uint32_t)p, &r, &c, &d) ? (uint32_t)c : (uint32_t)v.vocab;   // invalid slots sort last
+        ids[p] = (uint32_t)p;
+    }
+}
+__global__ void cooc_row_keys_kernel(const CoocView v, const uint32_t *__restrict__ ids, uint32_t *__restrict__ keys) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < v.n_pairs; q += (int64_t)gridDim.x * blockDim.x) {
+        int32_t r, c, d;
+        keys[q] = v.decode(ids[q], &r, &c, &d) ? (uint32_t)r : (uint32_t)v.vocab;
+    }
+}
+// head[q] = 1 when sorted slot q starts a new (row, col) cell
+__global__ void cooc_heads_kernel(const CoocView v, const uint32_t *__restrict__ ids, uint32_t *__restrict__ head) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < v.n_pairs; q += (int64_t)gridDim.x * blockDim.x) {
+        int32_t r, c, d, r0, c0, d0;
+        uint32_t h = 0;
+        if (v.decode(ids[q], &r, &c, &d)) h = (q == 0 || !v.decode(ids[q - 1], &r0, &c0, &d0) || r0 != r || c0 != c) ? 1u : 0u;
+        head[q] = h;
+    }
+}
+// one thread per cell: the cell's slots are contiguous and in corpus order; add 1.0 / distance one by one
+__global__ void cooc_sum_kernel(const CoocView v, const uint32_t *__restrict__ ids, const uint32_t *__restrict__ head,
+                                const int64_t *__restrict__ cell_of, int64_t capacity, int32_t *__restrict__ rows,
+                                int32_t *__restrict__ cols, double *__restrict__ vals) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < v.n_pairs; q += (int64_t)gridDim.x * blockDim.x) {
+        if (!head[q]) continue;
+        const int64_t cell = cell_of[q];
+        if (cell >= capacity) continue;
+        int32_t r, c, d;
+        v.decode(ids[q], &r, &c, &d);
+        double sum = 0.0;
+        int64_t t = q;
+        do {
+            int32_t r1, c1, d1;
+            if (!v.decode(ids[t], &r1, &c1, &d1)) break;    // the invalid tail
+            sum = __dadd_rn(sum, __ddiv_rn(1.0, (double)d1));               // glove.pyx:221
+            ++t;
+        } while (t < v.n_pairs && !head[t]);
+        rows[cell] = r;
+        cols[cell] = c;
+        vals[cell] = sum;
+    }
+}
+
+}  // namespace cymf
+
+extern "C" int64_t cymf_cooc_workspace_bytes(int64_t n_tokens, int32_t window) {
+    const int64_t P = n_tokens * (int64_t)window;
+    return (int64_t)(3 * align256((size_t)P * 4) + align256((size_t)(P + 1) * 8) + sort_workspace_bytes(P) +
+                     (size_t)cymf_scan_workspace_bytes(P));
+}
+
+// tokens[n_tokens]: kept-word ids of the corpus, lines concatenated; pos_in_line[n_tokens]: index of the token within
+// its line.  rows / cols / vals (capacity entries, <= n_tokens * window needed) receive the cells sorted by
+// (row, col); *nnz_out (DEVICE int64) the number of cells (entries beyond `capacity` are dropped, nnz_out still counts).
+extern "C" int cymf_cooc_count_dev(const int32_t *tokens, const int32_t *pos_in_line, int64_t n_tokens, int32_t vocab,
+                                   int32_t window, int32_t *rows, int32_t *cols, double *vals, int64_t capacity,
+                                   int64_t *nnz_out, void *workspace, void *stream) {
+    CYMF_REQUIRE(nnz_out && workspace && n_tokens >= 0 && vocab > 0 && window > 0 && capacity >= 0, "bad argument");
+    const int64_t P = n_tokens * (int64_t)window;
+    CYMF_REQUIRE(P < ((int64_t)1 << 32), "n_tokens * window_size must stay below 2^32");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P == 0) { CYMF_CUDA(cudaMemsetAsync(nnz_out, 0, 8, st)); return 0; }
+    CYMF_REQUIRE(tokens && pos_in_line && rows && cols && vals, "null pointer");
+    char *ws = (char *)workspace;
+    uint32_t *keys = (uint32_t *)ws; ws += align256((size_t)P * 4);
+    uint32_t *ids = (uint32_t *)ws; ws += align256((size_t)P * 4);
+    uint32_t *head = (uint32_t *)ws; ws += align256((size_t)P * 4);
+    int64_t *cell_of = (int64_t *)ws; ws += align256((size_t)(P + 1) * 8);
+    void *sort_ws = ws; ws += sort_workspace_bytes(P);
+    void *scan_ws = ws;
+    const CoocView v{tokens, pos_in_line, P, window, vocab};
+    const int bits = bits_for((int64_t)vocab + 1);
+    cooc_col_keys_kernel<<<flat_grid(P), 256, 0, st>>>(v, keys, ids);
+    CYMF_LAUNCHED();
+    CYMF_TRY(radix_sort_pairs(keys, ids, P, bits, sort_ws, st));
+    cooc_row_keys_kernel<<<flat_grid(P), 256, 0, st>>>(v, ids, keys);
+    CYMF_LAUNCHED();
+    CYMF_TRY(radix_sort_pairs(keys, ids, P, bits, sort_ws, st));
+    cooc_heads_kernel<<<flat_grid(P), 256, 0, st>>>(v, ids, head);
+    CYMF_LAUNCHED();
+    CYMF_TRY((exclusive_scan<uint32_t, int64_t>(head, cell_of, P, 1, (uint64_t *)scan_ws, st)));
+    CYMF_CUDA(cudaMemcpyAsync(nnz_out, cell_of + P, 8, cudaMemcpyDeviceToDevice, st));
+    cooc_sum_kernel<<<flat_grid(P), 256, 0, st>>>(v, ids, head, cell_of, capacity, rows, cols, vals);
+    CYMF_LAUNCHED();
+    return 0;
+}

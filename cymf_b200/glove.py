@@ -177,3 +177,59 @@ class GloveSession(object):
         """Algorithmic bytes per sample: 4 rows RW + 4 scalars RW + (c, x, count)."""
         s = 4 if self.dtype == _lib.F32 else 8
         return 8 * self.K * s + 8 * s + 8 + s
+
+
+def read_text(fname, min_count=5, window_size=10):
+    """`cymf.glove.read_text(fname, min_count, window_size)` (cymf/glove.pyx:183-241): co-occurrence matrix of a
+    text file -> (scipy.sparse.csr_matrix [V, V] float64, i2w dict).
+
+    The vocabulary pass is the reference's own Python, statement for statement (word counts over the text with
+    newlines glued as "<eos>", ids in first-appearance order of the words with count >= min_count, KeyError for a
+    word that only ever occurs next to a newline, glove.pyx:198-214).  The counting loop (glove.pyx:218-221, an
+    `unordered_map<long, double>` updated once per (token, earlier token within the window): 170 M updates for text8)
+    runs on the device: cymf_cooc_count_dev sorts the updates by cell with two stable radix sorts and sums every
+    cell in corpus order in f64, so the counts are bit-identical to the reference's."""
+    import torch
+    from collections import Counter
+    with open(fname) as f:
+        raw = f.read()
+        words = raw.replace("\n", "<eos>").split(" ")
+    count = dict(Counter(words))
+    lines = raw.split("\n")
+    w2i, i2w = {}, {}
+    tokens, pos = [], []
+    for line in lines:
+        n = 0
+        for w in line.split(" "):
+            if count[w] >= min_count:
+                index = w2i.get(w)
+                if index is None:
+                    index = len(w2i)
+                    w2i[w] = index
+                    i2w[index] = w
+                tokens.append(index)
+                pos.append(n)
+                n += 1
+    V = len(w2i)
+    T = len(tokens)
+    if V == 0 or T == 0:
+        return sparse.csr_matrix((V, V), dtype=np.float64), i2w
+    _lib.require_cuda()
+    L = _lib.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d_tok = torch.from_numpy(np.asarray(tokens, np.int32)).to(dev)
+    d_pos = torch.from_numpy(np.asarray(pos, np.int32)).to(dev)
+    cap = T * int(window_size)
+    rows = torch.empty(cap, dtype=torch.int32, device=dev)
+    cols = torch.empty(cap, dtype=torch.int32, device=dev)
+    vals = torch.empty(cap, dtype=torch.float64, device=dev)
+    nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = torch.empty(max(int(L.cymf_cooc_workspace_bytes(T, int(window_size))), 256), dtype=torch.uint8, device=dev)
+    _lib.check(L.cymf_cooc_count_dev(_lib.ptr(d_tok), _lib.ptr(d_pos), T, V, int(window_size), _lib.ptr(rows), _lib.ptr(cols),
+                                     _lib.ptr(vals), cap, _lib.ptr(nnz), _lib.ptr(ws), _lib.stream_ptr()))
+    m = int(nnz.item())
+    r, c, v = rows[:m].cpu().numpy(), cols[:m].cpu().numpy(), vals[:m].cpu().numpy()
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(r, minlength=V))]).astype(np.int32 if m < 2 ** 31 else np.int64)
+    X = sparse.csr_matrix((v, c, indptr), shape=(V, V))       # cells arrive sorted by (row, col): canonical CSR
+    X.has_sorted_indices = True
+    return X, i2w

@@ -9,6 +9,7 @@
  *   cymf_relmf_*        <- cymf/relmf.pyx:107-148   RelMF._fit_relmf  (+ cymf/model.pyx:99-142, cymf/optimizer.pyx)
  *   cymf_glove_*        <- cymf/glove.pyx:117-156   GloVe._fit_glove  (+ cymf/model.pyx:166-204, optimizer.pyx:85-123)
  *   cymf_als_*, cymf_gram_* <- cymf/wmf.pyx:136-174 WMF._als          (+ cymf/linalg.pyx:144-163 solvep)
+ *   cymf_cooc_*         <- cymf/glove.pyx:183-241   read_text (co-occurrence counting loop, :218-221)
  *   cymf_eval_*         <- cymf/evaluator.pyx:57-139 Evaluator.evaluate (+ cymf/metrics.pyx:24-125)
  *
  * Conventions
@@ -209,6 +210,18 @@ int64_t cymf_csr_block_workspace_bytes(int64_t count);
 int cymf_csr_block_dev(const int64_t *indptr, const int32_t *indices, const int64_t *slot_row, int64_t count,
                        const int64_t *col_slot, int64_t *blk_indptr, int32_t *blk_indices, void *workspace,
                        void *stream);
+
+/* ---- co-occurrence counting of read_text (cymf/glove.pyx:183-241, loop at :218-221) --------
+ * For every kept token j of a line and every earlier kept token k of the same line with j - k <= window:
+ * M[x_j, x_k] += 1.0 / (j - k).  tokens[n_tokens] = kept-word ids, lines concatenated; pos_in_line[n_tokens] = index
+ * of the token inside its line (both DEVICE int32).  Cells come out sorted by (row, col) in rows / cols / vals
+ * (`capacity` entries each; n_tokens * window always suffices), *nnz_out (DEVICE int64) = number of cells.  Every
+ * cell is summed in f64 in the reference's own order, so the counts are bit-identical to its unordered_map's.
+ * n_tokens * window must stay below 2^32. */
+int64_t cymf_cooc_workspace_bytes(int64_t n_tokens, int32_t window);
+int cymf_cooc_count_dev(const int32_t *tokens, const int32_t *pos_in_line, int64_t n_tokens, int32_t vocab,
+                        int32_t window, int32_t *rows, int32_t *cols, double *vals, int64_t capacity,
+                        int64_t *nnz_out, void *workspace, void *stream);
 
 /* ---- WMF ALS (cymf/wmf.pyx:136-174, cymf/linalg.pyx:144-163) ------------------------------------------- */
 /* G = Y^T Y (+ weight_decay * I when add_weight_decay != 0), wmf.pyx:142-143.  Y is [n, ld] of `dtype`.

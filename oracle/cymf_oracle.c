@@ -410,6 +410,64 @@ int oracle_glove_fit(const int32_t *central, const int32_t *context, const doubl
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Co-occurrence counting of read_text   (cymf/glove.pyx:218-221)
+ *   for every kept token j of a line, for k = max(0, j - window) .. j-1 (same line):
+ *       M[x_j + x_k * V] += 1.0 / (j - k)          (std::unordered_map<long, double>)
+ *   tokens: kept-word ids, lines concatenated; line_ptr[n_lines + 1]: offsets of the lines.
+ *   Cells are returned sorted by (row = x_j, col = x_k); every cell is summed in corpus order, as the
+ *   map does.  Returns the number of cells, or -1 (memory) / -2 (capacity).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { int64_t key; double val; } cooc_cell;
+static int cmp_cooc(const void *a, const void *b) {
+    int64_t x = ((const cooc_cell *)a)->key, y = ((const cooc_cell *)b)->key;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+int64_t oracle_cooc_count(const int32_t *tokens, const int64_t *line_ptr, int64_t n_lines, int32_t V, int32_t window,
+                          int32_t *rows, int32_t *cols, double *vals, int64_t capacity) {
+    int64_t cap = 1024, used = 0;
+    cooc_cell *tab = (cooc_cell *)malloc((size_t)cap * sizeof(cooc_cell));
+    if (!tab) return -1;
+    for (int64_t t = 0; t < cap; ++t) tab[t].key = -1;
+    for (int64_t l = 0; l < n_lines; ++l) {
+        const int32_t *x = tokens + line_ptr[l];
+        int64_t n = line_ptr[l + 1] - line_ptr[l];
+        for (int64_t j = 0; j < n; ++j)
+            for (int64_t k = (j - window > 0 ? j - window : 0); k < j; ++k) {
+                if (2 * (used + 1) > cap) {                                   /* grow and rehash */
+                    int64_t ncap = cap * 2;
+                    cooc_cell *nt = (cooc_cell *)malloc((size_t)ncap * sizeof(cooc_cell));
+                    if (!nt) { free(tab); return -1; }
+                    for (int64_t t = 0; t < ncap; ++t) nt[t].key = -1;
+                    for (int64_t t = 0; t < cap; ++t)
+                        if (tab[t].key >= 0) {
+                            uint64_t h = ((uint64_t)tab[t].key * 0x9E3779B97F4A7C15ull) & (uint64_t)(ncap - 1);
+                            while (nt[h].key >= 0) h = (h + 1) & (uint64_t)(ncap - 1);
+                            nt[h] = tab[t];
+                        }
+                    free(tab); tab = nt; cap = ncap;
+                }
+                /* key as the reference forms it, but row-major so that sorting by key is (row, col) order */
+                int64_t key = (int64_t)x[j] * V + x[k];
+                uint64_t h = ((uint64_t)key * 0x9E3779B97F4A7C15ull) & (uint64_t)(cap - 1);
+                while (tab[h].key >= 0 && tab[h].key != key) h = (h + 1) & (uint64_t)(cap - 1);
+                if (tab[h].key < 0) { tab[h].key = key; tab[h].val = 0.0; ++used; }
+                tab[h].val += 1.0 / (double)(j - k);                          /* glove.pyx:221 */
+            }
+    }
+    int64_t m = 0;
+    for (int64_t t = 0; t < cap; ++t) if (tab[t].key >= 0) tab[m++] = tab[t];
+    qsort(tab, (size_t)m, sizeof(cooc_cell), cmp_cooc);
+    if (m > capacity) { free(tab); return -2; }
+    for (int64_t t = 0; t < m; ++t) {
+        rows[t] = (int32_t)(tab[t].key / V);
+        cols[t] = (int32_t)(tab[t].key % V);
+        vals[t] = tab[t].val;
+    }
+    free(tab);
+    return m;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Evaluator   (cymf/evaluator.pyx:57-139, cymf/metrics.pyx:24-43,71-85,109-125), unbiased=False.
  *   Candidates of user u = its test positives (CSR order) followed by num_negatives items drawn
  *   with replacement from one sequential generator, rejecting test+train positives.

@@ -4,6 +4,7 @@ Each function mirrors the reference call it restates (file:line under /root/refe
   bpr_fit      <- cymf/bpr.pyx:117-171  (`BPR._fit_bpr`, num_threads=1)
   als_half     <- cymf/wmf.pyx:136-174  (`WMF._als`)
   glove_fit    <- cymf/glove.pyx:117-156 (`GloVe._fit_glove`)
+  read_text    <- cymf/glove.pyx:183-241 (co-occurrence builder)
   relmf_fit    <- cymf/relmf.pyx:107-148 (`RelMF._fit_relmf`, num_threads=1)
   evaluate     <- cymf/evaluator.pyx:57-139 (`Evaluator.evaluate`, unbiased=False)
   rng_*        <- cymf/math.pyx:12-18 (`UniformGenerator`)
@@ -60,6 +61,9 @@ def lib():
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                           C.c_double, C.c_double, C.c_double, C.c_void_p]
+        _lib.oracle_cooc_count.restype = C.c_int64
+        _lib.oracle_cooc_count.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         _lib.oracle_eval_candidates.restype = C.c_int64
         _lib.oracle_eval_candidates.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -222,6 +226,52 @@ def glove_fit(central, context, counts, W, bw, H, bh, num_epochs, lr, x_max, alp
     if rc:
         raise MemoryError("oracle_glove_fit")
     return ls
+
+
+def read_text_vocabulary(fname, min_count=5):
+    """The Python part of `read_text` (cymf/glove.pyx:198-214), statement for statement: word counts over the text with
+    newlines glued as "<eos>", ids in first-appearance order of the words kept.  Returns (list of id lists, i2w)."""
+    from collections import Counter
+    with open(fname) as f:
+        raw = f.read()
+        words = raw.replace("\n", "<eos>").split(" ")
+    count = dict(Counter(words))
+    lines = raw.split("\n")
+    w2i, i2w, x = {}, {}, []
+    for i in range(len(lines)):
+        words = lines[i].split(" ")
+        tmp = []
+        for j in range(len(words)):
+            if words[j] not in w2i and count[words[j]] >= min_count:
+                index = len(w2i)
+                w2i[words[j]] = index
+                i2w[index] = words[j]
+                tmp.append(index)
+            elif count[words[j]] >= min_count:
+                tmp.append(w2i[words[j]])
+        x.append(tmp)
+    return x, i2w
+
+
+def cooc_count(x, vocab_size, window_size):
+    """The counting loop of `read_text` (cymf/glove.pyx:218-221) -> (rows, cols, vals) sorted by (row, col)."""
+    tokens = np.ascontiguousarray(np.concatenate([np.asarray(t, np.int32) for t in x] + [np.empty(0, np.int32)]), np.int32)
+    line_ptr = np.concatenate([[0], np.cumsum([len(t) for t in x])]).astype(np.int64)
+    cap = int(tokens.shape[0]) * int(window_size) + 1
+    rows, cols, vals = np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.float64)
+    m = lib().oracle_cooc_count(_p(tokens), _p(line_ptr), len(x), vocab_size, window_size, _p(rows), _p(cols), _p(vals), cap)
+    if m < 0:
+        raise MemoryError("oracle_cooc_count")
+    return rows[:m].copy(), cols[:m].copy(), vals[:m].copy()
+
+
+def read_text(fname, min_count=5, window_size=10):
+    """`cymf.glove.read_text(fname, min_count, window_size)` (cymf/glove.pyx:183-241) -> (csr_matrix, i2w)."""
+    from scipy import sparse
+    x, i2w = read_text_vocabulary(fname, min_count)
+    V = len(i2w)
+    rows, cols, vals = cooc_count(x, max(V, 1), window_size)
+    return sparse.csr_matrix((vals, (rows, cols)), shape=(V, V)), i2w
 
 
 def eval_candidates(test, train, num_negatives=100, seed=1234):

@@ -173,6 +173,31 @@ def eval_case(U, I, nnz, K, seed):
     return out
 
 
+def write_corpus(path, n_words, vocab, seed, lines):
+    """Zipf-distributed pseudo text; with lines > 1, line boundaries are placed so that the words next to a newline
+    also occur inside lines (the reference counts words on the text with newlines glued as "<eos>", glove.pyx:199-200,
+    and would raise KeyError otherwise)."""
+    rng = np.random.default_rng(seed)
+    p = 1.0 / (np.arange(vocab) + 1.0)
+    ids = rng.choice(vocab, size=n_words, p=p / p.sum())
+    words = [f"w{i}" for i in ids]
+    per = n_words // lines
+    chunks = [words[q * per:(q + 1) * per] for q in range(lines)]
+    open(path, "w").write("\n".join(" ".join(c) for c in chunks))
+
+
+def cooc_case(fname, min_count, window):
+    """`cymf.glove.read_text` of the compiled reference on the committed corpus file."""
+    from cymf.glove import read_text
+    X, i2w = read_text(os.path.join(HERE, fname), min_count, window)
+    X = X.tocsr()
+    X.sum_duplicates()
+    X.sort_indices()
+    return dict(indptr=X.indptr.astype(np.int64), indices=X.indices.astype(np.int32), data=X.data,
+                shape=np.array(X.shape), words=np.array([i2w[i] for i in range(len(i2w))]),
+                min_count=min_count, window=window)
+
+
 def metric_vectors():
     rng = np.random.default_rng(5)
     ys, vals = [], []
@@ -197,6 +222,11 @@ def main():
         if not only or any(name.startswith(o) for o in only):
             np.savez_compressed(os.path.join(HERE, name), **make())
 
+    if not only or "cooc" in only:
+        write_corpus(os.path.join(HERE, "corpus_one_line.txt"), 6000, 300, seed=61, lines=1)      # text8-like
+        write_corpus(os.path.join(HERE, "corpus_lines.txt"), 4000, 60, seed=62, lines=5)
+    save("cooc_one_line.npz", lambda: cooc_case("corpus_one_line.txt", 5, 10))
+    save("cooc_lines.npz", lambda: cooc_case("corpus_lines.txt", 3, 4))
     save("rng64.npz", rng64_vectors)
     for opt in ("sgd", "adagrad", "adam"):
         save(f"relmf_{opt}.npz", lambda: relmf_case(30, 40, 300, 12, 2, 0.05, 0.01, 0.1, opt, seed=51))

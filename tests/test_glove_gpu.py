@@ -102,3 +102,39 @@ def test_fit_api_and_hogwild_f32_loss(oracle):
         cymf.GloVe(8).fit(np.eye(4), 1, 1)
     with pytest.raises(ValueError):
         cymf.GloVe(8).fit(None, 1, 1)
+
+
+@pytest.mark.parametrize("name,txt", [("cooc_one_line", "corpus_one_line.txt"), ("cooc_lines", "corpus_lines.txt")])
+def test_read_text_device_counts_bitwise(name, txt):
+    """cymf.glove.read_text: the unordered_map loop of glove.pyx:218-221 as two radix sorts + ordered cell sums."""
+    import os
+    from conftest import GOLDEN
+    import cymf_b200 as cymf
+    g = golden(name + ".npz")
+    X, i2w = cymf.glove.read_text(os.path.join(GOLDEN, txt), int(g["min_count"]), int(g["window"]))
+    assert X.shape == tuple(g["shape"]) and [i2w[i] for i in range(len(i2w))] == list(g["words"])
+    assert np.array_equal(X.indptr, g["indptr"]) and np.array_equal(X.indices, g["indices"])
+    assert np.array_equal(X.data, g["data"])                                   # f64 sums in the reference's order
+
+
+def test_read_text_larger_corpus_vs_oracle(oracle, tmp_path):
+    """200 k tokens, 2 k words, window 10 (2 M map updates): device counts == oracle, and a GloVe fit accepts them."""
+    import cymf_b200 as cymf
+    rng = np.random.default_rng(7)
+    p = 1.0 / (np.arange(2000) + 1.0)
+    ids = rng.choice(2000, size=200_000, p=p / p.sum())
+    f = tmp_path / "corpus.txt"
+    f.write_text(" ".join(f"w{i}" for i in ids))
+    X, i2w = cymf.glove.read_text(str(f), 5, 10)
+    Xo, i2wo = oracle.read_text(str(f), 5, 10)
+    Xo.sort_indices()
+    assert i2w == i2wo and X.shape == Xo.shape and X.nnz == Xo.nnz
+    assert np.array_equal(X.indptr, Xo.indptr) and np.array_equal(X.indices, Xo.indices)
+    assert np.array_equal(X.data, Xo.data)
+    m = cymf.GloVe(16, 0.05)
+    m.fit(X, 2, 1)
+    assert np.isfinite(m.W).all() and m.W.shape == (X.shape[0], 16)
+    with pytest.raises(KeyError):                                              # glove.pyx:199-209 quirk, kept
+        g = tmp_path / "bad.txt"
+        g.write_text("a b c\nd e f")
+        cymf.glove.read_text(str(g), 1, 2)

@@ -112,3 +112,16 @@ def test_metric_functions(oracle):
         y = row[2:2 + n]
         got = [oracle.metric_at_k(m, y, k) for m in ("DCG", "Recall", "MAP")]
         assert got == list(want)
+
+
+@pytest.mark.parametrize("name,txt", [("cooc_one_line", "corpus_one_line.txt"), ("cooc_lines", "corpus_lines.txt")])
+def test_read_text_bitwise(oracle, name, txt):
+    """`read_text` (cymf/glove.pyx:183-241): vocabulary order and every co-occurrence count, bit for bit."""
+    import os
+    from conftest import GOLDEN
+    g = golden(name + ".npz")
+    X, i2w = oracle.read_text(os.path.join(GOLDEN, txt), int(g["min_count"]), int(g["window"]))
+    X.sort_indices()
+    assert X.shape == tuple(g["shape"]) and [i2w[i] for i in range(len(i2w))] == list(g["words"])
+    assert np.array_equal(X.indptr, g["indptr"]) and np.array_equal(X.indices, g["indices"])
+    assert np.array_equal(X.data, g["data"])
