@@ -45,26 +45,30 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def dataset(name):
-    """(train CSR, users, positives) of a MovieLens shape; cached on local disk between invocations."""
+def dataset(name, with_test=False):
+    """(train CSR, users, positives) of a MovieLens shape -- or (train, held-out test) -- cached on local disk."""
     from scipy import sparse
     from sklearn import utils
     from cymf_b200 import synth
     os.makedirs(CACHE, exist_ok=True)
-    f = os.path.join(CACHE, f"{name}.npz")
+    f = os.path.join(CACHE, f"{name}_v2.npz")
     if os.path.exists(f):
         z = np.load(f)
         train = sparse.csr_matrix((np.ones(z["indices"].shape[0]), z["indices"], z["indptr"]), shape=tuple(z["shape"]))
+        if with_test:
+            test = sparse.csr_matrix((np.ones(z["test_indices"].shape[0]), z["test_indices"], z["test_indptr"]),
+                                     shape=tuple(z["shape"]))
+            return train, test
         return train, z["users"], z["positives"]
-    train, _ = synth.movielens_like(name)
+    train, test = synth.movielens_like(name)
     np.random.seed(4321)
     users, positives = utils.shuffle(*train.nonzero())          # bpr.pyx:104
     users, positives = users.astype(np.int32), positives.astype(np.int32)
     tmp = f + f".{os.getpid()}.tmp.npz"
     np.savez(tmp, indptr=train.indptr, indices=train.indices, shape=np.array(train.shape), users=users,
-             positives=positives)
+             positives=positives, test_indptr=test.indptr, test_indices=test.indices)
     os.replace(tmp, f)
-    return train, users, positives
+    return (train, test) if with_test else (train, users, positives)
 
 
 class ClockSampler(threading.Thread):
@@ -147,6 +151,52 @@ def time_relmf_device(train, K, optimizer, steps, warmup, hbm, samples, dtype="f
     return {"samples_per_s": samples / sec, "ms_per_epoch": 1e3 * sec, "samples_per_epoch": samples,
             "cells": int(train.shape[0]) * int(train.shape[1]), "K": K, "optimizer": optimizer,
             "algorithmic_GBps": gbps, "frac_of_hbm_peak": gbps / hbm}
+
+
+def time_evaluator(name, K, steps, hbm, with_reference):
+    """`AverageOverAllEvaluator(test, train, k=5).evaluate(W, H)` (cymf/evaluator.pyx:57-139) on device-resident
+    factors: per-user candidate scoring, exact ranking, DCG/Recall/MAP@5.  Candidate lists (host mt19937 stream) are
+    built once per seed and timed separately."""
+    import torch
+    import cymf_b200 as cymf
+    train, test = dataset(name, with_test=True)
+    U, I = train.shape
+    ev = cymf.evaluator.AverageOverAllEvaluator(test, train, k=5)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1)
+    W = torch.randn((U, K), dtype=torch.float64, device="cuda", generator=g)
+    H = torch.randn((I, K), dtype=torch.float64, device="cuda", generator=g)
+    t0 = time.perf_counter()
+    res = ev.evaluate(W, H)                                   # builds + uploads the candidate lists
+    torch.cuda.synchronize()
+    first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = ev.evaluate(W, H)
+    torch.cuda.synchronize()
+    sec = (time.perf_counter() - t0) / steps
+    cand_ptr, _ = ev.candidates()
+    n_cand = int(cand_ptr[-1])
+    algo = n_cand * (8 * K + 4) + 8 * U * K                   # SURVEY.md 8(d): gathered H rows + candidate ids + W
+    out = {"sec_per_call": sec, "users_per_s": U / sec, "candidates": n_cand, "K": K, "shape": [U, I],
+           "first_call_sec_incl_candidate_lists": first, "algorithmic_GBps": algo / sec / 1e9,
+           "frac_of_hbm_peak": algo / sec / 1e9 / hbm, "DCG@5_random_factors": res["DCG@5"],
+           "note": "wall clock around evaluate(): kernel + D2H of the per-user metrics + NumPy mean"}
+    if with_reference:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+            import cymf as ref
+            rows = 4000
+            rev = ref.evaluator.AverageOverAllEvaluator(test[:rows], train[:rows], k=5)
+            Wc, Hc = W[:rows].cpu().numpy(), H.cpu().numpy()
+            t0 = time.perf_counter()
+            rev.evaluate(Wc, Hc)
+            out["reference_users_per_s"] = rows / (time.perf_counter() - t0)
+            out["reference_sample"] = f"compiled reference Evaluator.evaluate on the first {rows} users"
+        except Exception as ex:                              # noqa: BLE001
+            out["reference_users_per_s"] = None
+            out["reference_sample"] = f"failed: {ex}"
+    return out
 
 
 def time_bpr_e2e(train, users, positives, K, optimizer, steps, warmup, lr=LR, wd=WD):
@@ -385,6 +435,7 @@ def main():
                           "frac_of_hbm_peak": a_ * ss.bytes_per_update / s_ / 1e9 / hbm}
             del ss
             torch.cuda.empty_cache()
+        extra["evaluator_ml20m_k128"] = time_evaluator("ml-20m", 128, 3, hbm, with_reference=(world == 1 and not args.no_cpu))
         for tag, opt in (("relmf_sgd_f32_k128", "sgd"), ("relmf_adam_f32_k128", "adam")):
             extra[tag] = time_relmf_device(train, 128, opt, max(3, args.steps // 2), 3, hbm, 50_000_000)
             torch.cuda.empty_cache()

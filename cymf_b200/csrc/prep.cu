@@ -436,20 +436,33 @@ __global__ void cooc_row_keys_kernel(const CoocView v, const uint32_t *__restric
         keys[q] = v.decode(ids[q], &r, &c, &d) ? (uint32_t)r : (uint32_t)v.vocab;
     }
 }
-// head[q] = 1 when sorted slot q starts a new (row, col) cell
-__global__ void cooc_heads_kernel(const CoocView v, const uint32_t *__restrict__ ids, uint32_t *__restrict__ head) {
+// head[q] = 1 when sorted slot q starts a new (row, col) cell; *n_valid = number of valid slots (they sort first)
+__global__ void cooc_heads_kernel(const CoocView v, const uint32_t *__restrict__ ids, uint32_t *__restrict__ head,
+                                  int64_t *__restrict__ n_valid) {
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < v.n_pairs; q += (int64_t)gridDim.x * blockDim.x) {
         int32_t r, c, d, r0, c0, d0;
         uint32_t h = 0;
-        if (v.decode(ids[q], &r, &c, &d)) h = (q == 0 || !v.decode(ids[q - 1], &r0, &c0, &d0) || r0 != r || c0 != c) ? 1u : 0u;
+        if (v.decode(ids[q], &r, &c, &d)) {
+            h = (q == 0 || !v.decode(ids[q - 1], &r0, &c0, &d0) || r0 != r || c0 != c) ? 1u : 0u;
+            if (q + 1 == v.n_pairs || !v.decode(ids[q + 1], &r0, &c0, &d0)) *n_valid = q + 1;   // exactly one such q
+        }
         head[q] = h;
     }
 }
-// one thread per cell: the cell's slots are contiguous and in corpus order; add 1.0 / distance one by one
+// One thread per cell: the cell's slots are contiguous and in corpus order; 1.0 / distance is added one by one
+// (glove.pyx:221) -- f64 addition is not associative, so the order IS the result.  The inner loop touches only the
+// two streamed arrays (ids, head) and a shared table of reciprocals: the chain of dependent additions of the most
+// frequent cell (~1 % of all updates for a Zipf corpus) is what bounds the kernel.
 __global__ void cooc_sum_kernel(const CoocView v, const uint32_t *__restrict__ ids, const uint32_t *__restrict__ head,
-                                const int64_t *__restrict__ cell_of, int64_t capacity, int32_t *__restrict__ rows,
-                                int32_t *__restrict__ cols, double *__restrict__ vals) {
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < v.n_pairs; q += (int64_t)gridDim.x * blockDim.x) {
+                                const int64_t *__restrict__ cell_of, const int64_t *__restrict__ n_valid_ptr,
+                                int64_t capacity, int32_t *__restrict__ rows, int32_t *__restrict__ cols,
+                                double *__restrict__ vals) {
+    extern __shared__ double recip[];                       // recip[s] = 1.0 / (window - s), s = slot % window
+    for (int s = threadIdx.x; s < v.window; s += blockDim.x) recip[s] = __ddiv_rn(1.0, (double)(v.window - s));
+    __syncthreads();
+    const int64_t n_valid = *n_valid_ptr;
+    const uint32_t window = (uint32_t)v.window;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_valid; q += (int64_t)gridDim.x * blockDim.x) {
         if (!head[q]) continue;
         const int64_t cell = cell_of[q];
         if (cell >= capacity) continue;
@@ -458,11 +471,9 @@ __global__ void cooc_sum_kernel(const CoocView v, const uint32_t *__restrict__ i
         double sum = 0.0;
         int64_t t = q;
         do {
-            int32_t r1, c1, d1;
-            if (!v.decode(ids[t], &r1, &c1, &d1)) break;    // the invalid tail
-            sum = __dadd_rn(sum, __ddiv_rn(1.0, (double)d1));               // glove.pyx:221
+            sum = __dadd_rn(sum, recip[ids[t] % window]);
             ++t;
-        } while (t < v.n_pairs && !head[t]);
+        } while (t < n_valid && !head[t]);
         rows[cell] = r;
         cols[cell] = c;
         vals[cell] = sum;
@@ -474,7 +485,7 @@ __global__ void cooc_sum_kernel(const CoocView v, const uint32_t *__restrict__ i
 extern "C" int64_t cymf_cooc_workspace_bytes(int64_t n_tokens, int32_t window) {
     const int64_t P = n_tokens * (int64_t)window;
     return (int64_t)(3 * align256((size_t)P * 4) + align256((size_t)(P + 1) * 8) + sort_workspace_bytes(P) +
-                     (size_t)cymf_scan_workspace_bytes(P));
+                     (size_t)cymf_scan_workspace_bytes(P) + 256);
 }
 
 // tokens[n_tokens]: kept-word ids of the corpus, lines concatenated; pos_in_line[n_tokens]: index of the token within
@@ -495,7 +506,9 @@ extern "C" int cymf_cooc_count_dev(const int32_t *tokens, const int32_t *pos_in_
     uint32_t *head = (uint32_t *)ws; ws += align256((size_t)P * 4);
     int64_t *cell_of = (int64_t *)ws; ws += align256((size_t)(P + 1) * 8);
     void *sort_ws = ws; ws += sort_workspace_bytes(P);
-    void *scan_ws = ws;
+    void *scan_ws = ws; ws += (size_t)cymf_scan_workspace_bytes(P);
+    int64_t *n_valid = (int64_t *)ws;
+    CYMF_CUDA(cudaMemsetAsync(n_valid, 0, 8, st));
     const CoocView v{tokens, pos_in_line, P, window, vocab};
     const int bits = bits_for((int64_t)vocab + 1);
     cooc_col_keys_kernel<<<flat_grid(P), 256, 0, st>>>(v, keys, ids);
@@ -504,11 +517,11 @@ extern "C" int cymf_cooc_count_dev(const int32_t *tokens, const int32_t *pos_in_
     cooc_row_keys_kernel<<<flat_grid(P), 256, 0, st>>>(v, ids, keys);
     CYMF_LAUNCHED();
     CYMF_TRY(radix_sort_pairs(keys, ids, P, bits, sort_ws, st));
-    cooc_heads_kernel<<<flat_grid(P), 256, 0, st>>>(v, ids, head);
+    cooc_heads_kernel<<<flat_grid(P), 256, 0, st>>>(v, ids, head, n_valid);
     CYMF_LAUNCHED();
     CYMF_TRY((exclusive_scan<uint32_t, int64_t>(head, cell_of, P, 1, (uint64_t *)scan_ws, st)));
     CYMF_CUDA(cudaMemcpyAsync(nnz_out, cell_of + P, 8, cudaMemcpyDeviceToDevice, st));
-    cooc_sum_kernel<<<flat_grid(P), 256, 0, st>>>(v, ids, head, cell_of, capacity, rows, cols, vals);
+    cooc_sum_kernel<<<flat_grid(P), 256, (size_t)window * 8, st>>>(v, ids, head, cell_of, n_valid, capacity, rows, cols, vals);
     CYMF_LAUNCHED();
     return 0;
 }
