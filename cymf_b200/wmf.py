@@ -162,6 +162,7 @@ class AlsSession(object):
                  prep="device", overlap_classes=True, heavy_min=4096):
         torch = _lib.require_cuda()
         self.heavy_min = int(heavy_min)
+        self.tail_divisor = int(os.environ.get("CYMF_ALS_TAIL_DIVISOR", "256"))     # tuning hook (tools/c5_als.py)
         self.peer_error = None
         self._unperm = {}
         self.force_width = int(force_width)
@@ -340,7 +341,7 @@ class AlsSession(object):
             # out as a tail: row time >= ~half of the block's time (~0.45 ns per entry)  <=>  n >= block nnz / 256.
             # Measured: ml-20m on one GPU has no such row (19.4 ms/epoch either way, 22.2 ms with a floor of 4096);
             # sharded over 8 GPUs the same rows are 8x larger relative to their block and do qualify.
-            floor = max(self.heavy_min, int(lengths.sum()) // 256)
+            floor = max(self.heavy_min, int(lengths.sum()) // self.tail_divisor)
             while True:                                        # keep the slab workspace under 8 GB
                 nh = int((lengths >= floor).sum())             # a prefix: lengths are sorted in decreasing order
                 slabs = int(((lengths[:nh] + 511) // 512).sum())
