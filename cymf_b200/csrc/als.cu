@@ -189,6 +189,61 @@ __device__ __forceinline__ void warp_allsum4(T &d0, T &d1, T &d2, T &d3, int lan
 }
 constexpr int CG_VEC = 128;           // capacity of the shared K-vectors (ld <= 128)
 
+// acc + d0 y0 + d1 y1 + d2 y2 + d3 y3 as one chain of four fused multiply-adds (the CG kernel is issue-bound on
+// short rows -- 73 % issue-active, profiles/r1_als_cg_c5_scale03_ncu_full.txt -- and the pairwise form cost six
+// instructions per element instead of four)
+#define CYMF_AXPY4(a, d0, y0, d1, y1, d2, y2, d3, y3) fma_t(d3, y3, fma_t(d2, y2, fma_t(d1, y1, fma_t(d0, y0, a))))
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+
+// (lo, hi) += (y_lo, y_hi) * d as ONE packed instruction (Blackwell FFMA2, PTX fma.rn.f32x2): two independent IEEE
+// fused multiply-adds, so the values are those of the scalar chain.
+__device__ __forceinline__ void fma2_acc(float &lo, float &hi, float y_lo, float y_hi, float d) {
+    unsigned long long acc, y, dd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(acc) : "f"(lo), "f"(hi));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(y_lo), "f"(y_hi));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(dd) : "f"(d));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(y), "l"(dd));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc));
+}
+// y . p over the lane's slice: packed products, one horizontal add at the end
+template <typename T, int VW> __device__ __forceinline__ T dot_slice(const T (&y)[VW], const T (&p)[VW]) {
+    if constexpr (sizeof(T) == 4 && VW == 4) {
+        float lo = 0.f, hi = 0.f;
+        unsigned long long acc, a, b;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(y[0]), "f"(y[1]));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(p[0]), "f"(p[1]));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(a), "l"(b));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(y[2]), "f"(y[3]));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(p[2]), "f"(p[3]));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc));
+        return lo + hi;
+    } else {
+        T d = T(0);
+#pragma unroll
+        for (int e = 0; e < VW; ++e) d += y[e] * p[e];
+        return d;
+    }
+}
+// acc[:] += d0 y0[:] + d1 y1[:] + d2 y2[:] + d3 y3[:]
+template <typename T, int VW>
+__device__ __forceinline__ void axpy4(T (&acc)[VW], T d0, const T (&y0)[VW], T d1, const T (&y1)[VW], T d2,
+                                      const T (&y2)[VW], T d3, const T (&y3)[VW]) {
+    if constexpr (sizeof(T) == 4 && VW % 2 == 0) {
+#pragma unroll
+        for (int e = 0; e < VW; e += 2) {
+            fma2_acc(acc[e], acc[e + 1], y0[e], y0[e + 1], d0);
+            fma2_acc(acc[e], acc[e + 1], y1[e], y1[e + 1], d1);
+            fma2_acc(acc[e], acc[e + 1], y2[e], y2[e + 1], d2);
+            fma2_acc(acc[e], acc[e + 1], y3[e], y3[e + 1], d3);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < VW; ++e) acc[e] = CYMF_AXPY4(acc[e], d0, y0[e], d1, y1[e], d2, y2[e], d3, y3[e]);
+    }
+}
+
 // NW warps cooperate on one row.  VW = elements of a K-vector per lane (1: ld<=32, 2: ld<=64, 4: ld<=128).
 template <typename T, int VW, int NW>
 __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
@@ -291,13 +346,10 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
                 ld_vec<VW>(s, y0); ld_vec<VW>(s + NW * ld, y1);                                    \
                 ld_vec<VW>(s + 2 * NW * ld, y2); ld_vec<VW>(s + 3 * NW * ld, y3);                  \
             }                                                                                      \
-            T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);                                          \
-            _Pragma("unroll") for (int e = 0; e < VW; ++e) {                                       \
-                d0 += y0[e] * ps[e]; d1 += y1[e] * ps[e]; d2 += y2[e] * ps[e]; d3 += y3[e] * ps[e]; \
-            }                                                                                      \
+            T d0 = dot_slice<T, VW>(y0, ps), d1 = dot_slice<T, VW>(y1, ps), d2 = dot_slice<T, VW>(y2, ps),      \
+              d3 = dot_slice<T, VW>(y3, ps);                                                       \
             warp_allsum4(d0, d1, d2, d3, lane);                                                    \
-            _Pragma("unroll") for (int e = 0; e < VW; ++e)                                         \
-                acc[e] += (d0 * y0[e] + d1 * y1[e]) + (d2 * y2[e] + d3 * y3[e]);                   \
+            axpy4<T, VW>(acc, d0, y0, d1, y1, d2, y2, d3, y3);                                     \
         }                                                                                          \
         if (i < ns) { CYMF_MIXED_GROUP(); i += 4 * NW; }        /* the group that straddles the staging limit */ \
         if (i + 3 * NW < nnz) {                                 /* streamed groups, next group's gathers in flight */ \
@@ -320,13 +372,10 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
                     ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + 2 * NW) * ld, n2);                    \
                     ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + 3 * NW) * ld, n3);                    \
                 }                                                                                  \
-                T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);                                      \
-                _Pragma("unroll") for (int e = 0; e < VW; ++e) {                                   \
-                    d0 += y0[e] * ps[e]; d1 += y1[e] * ps[e]; d2 += y2[e] * ps[e]; d3 += y3[e] * ps[e]; \
-                }                                                                                  \
+                T d0 = dot_slice<T, VW>(y0, ps), d1 = dot_slice<T, VW>(y1, ps),                    \
+                  d2 = dot_slice<T, VW>(y2, ps), d3 = dot_slice<T, VW>(y3, ps);                    \
                 warp_allsum4(d0, d1, d2, d3, lane);                                                \
-                _Pragma("unroll") for (int e = 0; e < VW; ++e)                                     \
-                    acc[e] += (d0 * y0[e] + d1 * y1[e]) + (d2 * y2[e] + d3 * y3[e]);               \
+                axpy4<T, VW>(acc, d0, y0, d1, y1, d2, y2, d3, y3);                                 \
                 if (!more) break;                                                                  \
             }                                                                                      \
         }                                                                                          \
@@ -351,13 +400,10 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
                 if (i3 < ns) ld_vec<VW>(Ys + i3 * ld + kq, y3);                                    \
                 else if (i3 < nnz) ldg_vec<VW>(Yq + (size_t)__ldg(idx + i3) * ld, y3);             \
             }                                                                                      \
-            T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);                                          \
-            _Pragma("unroll") for (int e = 0; e < VW; ++e) {                                       \
-                d0 += y0[e] * ps[e]; d1 += y1[e] * ps[e]; d2 += y2[e] * ps[e]; d3 += y3[e] * ps[e]; \
-            }                                                                                      \
+            T d0 = dot_slice<T, VW>(y0, ps), d1 = dot_slice<T, VW>(y1, ps), d2 = dot_slice<T, VW>(y2, ps),      \
+              d3 = dot_slice<T, VW>(y3, ps);                                                       \
             warp_allsum4(d0, d1, d2, d3, lane);                                                    \
-            _Pragma("unroll") for (int e = 0; e < VW; ++e)                                         \
-                acc[e] += (d0 * y0[e] + d1 * y1[e]) + (d2 * y2[e] + d3 * y3[e]);                   \
+            axpy4<T, VW>(acc, d0, y0, d1, y1, d2, y2, d3, y3);                                     \
         }
 
 // + rows [j0, j1) of G p (untransformed solvers), publish the warp's partial, barrier, combine
@@ -412,18 +458,14 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
                     if (i + 2 * NW < ns) st_vec<VW>(Ys + (i + 2 * NW) * ld + kq, c2);
                     if (i + 3 * NW < ns) st_vec<VW>(Ys + (i + 3 * NW) * ld + kq, c3);
                 }
-                T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
 #pragma unroll
-                for (int e = 0; e < VW; ++e) {
-                    bacc[e] += (c0[e] + c1[e]) + (c2[e] + c3[e]);
-                    d0 += c0[e] * ps[e]; d1 += c1[e] * ps[e]; d2 += c2[e] * ps[e]; d3 += c3[e] * ps[e];
-                }
+                for (int e = 0; e < VW; ++e) bacc[e] += (c0[e] + c1[e]) + (c2[e] + c3[e]);
+                T d0 = dot_slice<T, VW>(c0, ps), d1 = dot_slice<T, VW>(c1, ps), d2 = dot_slice<T, VW>(c2, ps),
+                  d3 = dot_slice<T, VW>(c3, ps);
                 warp_allsum4(d0, d1, d2, d3, lane);
+                axpy4<T, VW>(acc, d0, c0, d1, c1, d2, c2, d3, c3);
 #pragma unroll
-                for (int e = 0; e < VW; ++e) {
-                    acc[e] += (d0 * c0[e] + d1 * c1[e]) + (d2 * c2[e] + d3 * c3[e]);
-                    c0[e] = n0[e]; c1[e] = n1[e]; c2[e] = n2[e]; c3[e] = n3[e];
-                }
+                for (int e = 0; e < VW; ++e) { c0[e] = n0[e]; c1[e] = n1[e]; c2[e] = n2[e]; c3[e] = n3[e]; }
             }
 #undef CYMF_GATHER4
             if (lane_on) st_vec<VW>(part + warp * CG_VEC + kq, bacc);
