@@ -199,6 +199,49 @@ def time_evaluator(name, K, steps, hbm, with_reference):
     return out
 
 
+def time_als_device_pipeline(scale, K, steps, hbm):
+    """BASELINE configs[4] pipeline at `scale` of 10 M x 1 M x 1 B nnz on ONE GPU: matrix generated on the device,
+    X^T / row deal / blocks by prep.cu, device-initialised factors (tools/c5_als.py runs the full size, 1-8 GPUs)."""
+    import torch
+    from cymf_b200 import _lib
+    from cymf_b200.synth import synth_implicit_device
+    from cymf_b200.wmf import AlsSession
+    U, I, nnz = int(10_000_000 * scale), int(1_000_000 * scale), int(1_000_000_000 * scale)
+    ip, ix = synth_implicit_device(U, I, nnz, seed=104)
+    real_nnz = int(ix.numel())
+    g = torch.Generator(device="cuda")
+    g.manual_seed(4321)
+    ld = _lib.ld_for(K)
+    W = (torch.rand((U, ld), device="cuda", generator=g) * 0.2 - 0.1) / K
+    H = (torch.rand((I, ld), device="cuda", generator=g) * 0.2 - 0.1) / K
+    W[:, K:] = 0
+    H[:, K:] = 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    s = AlsSession((ip, ix, (U, I)), W, H, 0.01, 10.0, K=K, distributed=False)
+    torch.cuda.synchronize()
+    prep_s = time.perf_counter() - t0
+    del W, H, ip, ix
+    for _ in range(2):
+        s.epoch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        s.epoch()
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / steps
+    algo = 2 * real_nnz * (K * 4 + 4) + (U + I) * (K * 4 + 8) + (U + I) * K * 4
+    out = {"sec_per_epoch": sec, "shape": [U, I], "nnz": real_nnz, "K": K, "prepare_on_device_sec": prep_s,
+           "algorithmic_GBps": algo / sec / 1e9, "frac_of_hbm_peak": algo / sec / 1e9 / hbm,
+           "unconverged_rows": s.stats()[1],
+           "full_size": "tools/c5_als.py: 0.90 s/epoch on 1 B200, 0.168 s on 8 (profiles/r1_c5_als_*.json)"}
+    del s
+    torch.cuda.empty_cache()
+    return out
+
+
 def time_bpr_e2e(train, users, positives, K, optimizer, steps, warmup, lr=LR, wd=WD):
     """Through the typed boundary with host buffers: every step uploads inputs and downloads the factors."""
     import torch
@@ -435,6 +478,7 @@ def main():
                           "frac_of_hbm_peak": a_ * ss.bytes_per_update / s_ / 1e9 / hbm}
             del ss
             torch.cuda.empty_cache()
+        extra["wmf_als_f32_k128_c5_scale0.1"] = time_als_device_pipeline(0.1, 128, 3, hbm)
         extra["evaluator_ml20m_k128"] = time_evaluator("ml-20m", 128, 3, hbm, with_reference=(world == 1 and not args.no_cpu))
         for tag, opt in (("relmf_sgd_f32_k128", "sgd"), ("relmf_adam_f32_k128", "adam")):
             extra[tag] = time_relmf_device(train, 128, opt, max(3, args.steps // 2), 3, hbm, 50_000_000)

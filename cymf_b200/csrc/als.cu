@@ -20,6 +20,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cymf {
@@ -645,6 +647,10 @@ template <typename T, int VW, int NW> static int launch_cg(AlsArgs<T> a, int32_t
     int per_sm = 0;
     CYMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * NW, smem));
     if (per_sm < 1) per_sm = 1;
+    if (const char *cap = getenv(NW == 4 ? "CYMF_ALS_CTAS4" : (NW == 8 ? "CYMF_ALS_CTAS8" : "CYMF_ALS_CTAS16"))) {
+        const int c = atoi(cap);                       // tuning hook: resident CTAs per SM for this row class
+        if (c >= 1 && c < per_sm) per_sm = c;
+    }
     int64_t blocks = (int64_t)sm_count() * per_sm;
     if (blocks > a.n_solve) blocks = a.n_solve;
     if (blocks < 1) blocks = 1;

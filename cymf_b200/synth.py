@@ -105,3 +105,37 @@ def synth_cooc(V, nnz, seed):
     X = sparse.csr_matrix((counts, (keys // V, keys % V)), shape=(V, V))
     X.sort_indices()
     return X
+
+
+def synth_implicit_device(U, I, nnz, seed, block_users=500_000, clusters=64):
+    """Device-side generator for matrices that never exist on the host (BASELINE configs[4]: 10 M x 1 M x 1 B nnz).
+    Returns CSR (indptr int64, indices int32; rows sorted, deduplicated) as torch tensors on the current CUDA device:
+    lognormal(sigma=1) user activity, item popularity ~ rank^-1/2, half of every user's items drawn from its taste
+    cluster (u mod 64).  Identical on every rank for the same seed (torch's Philox stream)."""
+    import torch
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    mean_deg = nnz / U
+    lens, idx = [], []
+    for lo in range(0, U, block_users):
+        n = min(block_users, U - lo)
+        act = torch.exp(torch.randn(n, device=dev, generator=g))
+        deg = torch.clamp(torch.round(act * (mean_deg / 1.6487) * 1.06), 1, I // 4).to(torch.int64)   # E[lognormal] = e^0.5
+        rows = torch.repeat_interleave(torch.arange(lo, lo + n, device=dev), deg)
+        v = torch.rand(rows.numel(), device=dev, generator=g)
+        in_cluster = torch.rand(rows.numel(), device=dev, generator=g) < 0.5
+        per = I // clusters
+        pop_all = torch.clamp((v * v * I).to(torch.int64), max=I - 1)
+        pop_clu = torch.clamp((v * v * per).to(torch.int64), max=per - 1) * clusters + rows % clusters
+        items = torch.where(in_cluster, torch.clamp(pop_clu, max=I - 1), pop_all)
+        keys = torch.unique(rows * I + items)                       # sorted, duplicates removed
+        lens.append(torch.bincount(torch.div(keys, I, rounding_mode="floor") - lo, minlength=n))
+        idx.append((keys % I).to(torch.int32))
+        del keys, rows, v, items, pop_all, pop_clu, in_cluster
+    lens = torch.cat(lens)
+    indptr = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens, 0)])
+    return indptr, torch.cat(idx)
+
+

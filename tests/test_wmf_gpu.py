@@ -123,3 +123,31 @@ def test_heavy_rows_direct_solve(oracle, K):
         for got, want in ((m.W, Wo), (m.H, Ho)):
             assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max(), (heavy_min, np.abs(got - want).max())
     assert np.abs(out[0][0] - out[100][0]).max() <= 2e-5 * np.abs(Wo).max()
+
+
+def test_device_generated_matrix_normal_equations(monkeypatch):
+    """The C5 pipeline at 1/100 scale (100 k x 10 k, ~8.6 M nnz; tools/c5_als.py): matrix generated on the device,
+    X^T / deal / blocks by prep.cu, factors initialised on the device, and after each half sweep the sampled rows
+    (plus the heaviest one) satisfy the reference's normal equations (cymf/wmf.pyx:161-168) in f64."""
+    import os
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import c5_als
+    from cymf_b200.synth import synth_implicit_device
+    from cymf_b200.wmf import AlsSession
+    U, I, K = 100_000, 10_000, 64
+    ip, ix = synth_implicit_device(U, I, 10_000_000, seed=104)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(4321)
+    W = (torch.rand((U, K), device="cuda", generator=g) * 0.2 - 0.1) / K
+    H = (torch.rand((I, K), device="cuda", generator=g) * 0.2 - 0.1) / K
+    monkeypatch.setenv("CYMF_ALS_TAIL_DIVISOR", "4096")    # rows of >= 2.1 k entries take the direct solve here
+    sess = AlsSession((ip, ix, (U, I)), W, H, 0.01, 10.0, K=K, heavy_min=2048)
+    assert sess.heavy_i is not None and sess.heavy_i[0] > 10
+    sess.epoch()
+    sess.user_half()
+    assert c5_als.residuals(sess, "user", 12, seed=0) <= 1e-4
+    sess.item_half()
+    assert c5_als.residuals(sess, "item", 12, seed=1) <= 1e-4
+    assert sess.stats()[1] == 0                            # no row stopped at cg_max_iter

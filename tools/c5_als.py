@@ -22,37 +22,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch  # noqa: E402
 
-
-def synth_c5_device(U, I, nnz, seed, block_users=500_000, clusters=64):
-    """CSR (indptr int64, indices int32, sorted, deduplicated) on the current device: lognormal(sigma=1) user
-    activity, item popularity ~ rank^-1/2, half of every user's items drawn from its taste cluster (u mod 64)."""
-    dev = torch.device("cuda", torch.cuda.current_device())
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed)
-    mean_deg = nnz / U
-    lens, idx = [], []
-    for lo in range(0, U, block_users):
-        n = min(block_users, U - lo)
-        act = torch.exp(torch.randn(n, device=dev, generator=g))
-        deg = torch.clamp(torch.round(act * (mean_deg / 1.6487) * 1.06), 1, I // 4).to(torch.int64)   # E[lognormal] = e^0.5
-        rows = torch.repeat_interleave(torch.arange(lo, lo + n, device=dev), deg)
-        v = torch.rand(rows.numel(), device=dev, generator=g)
-        in_cluster = torch.rand(rows.numel(), device=dev, generator=g) < 0.5
-        per = I // clusters
-        pop_all = torch.clamp((v * v * I).to(torch.int64), max=I - 1)
-        pop_clu = torch.clamp((v * v * per).to(torch.int64), max=per - 1) * clusters + rows % clusters
-        items = torch.where(in_cluster, torch.clamp(pop_clu, max=I - 1), pop_all)
-        keys = torch.unique(rows * I + items)                       # sorted, duplicates removed
-        lens.append(torch.bincount(torch.div(keys, I, rounding_mode="floor") - lo, minlength=n))
-        idx.append((keys % I).to(torch.int32))
-        del keys, rows, v, items, pop_all, pop_clu, in_cluster
-    lens = torch.cat(lens)
-    indptr = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens, 0)])
-    return indptr, torch.cat(idx)
+from cymf_b200.synth import synth_implicit_device as synth_c5_device  # noqa: E402
 
 
 def residuals(sess, side, sample, seed):
-    """Relative residual of the reference's normal equations for `sample` random rows of the block just solved."""
+    """Checker for sizes no CPU oracle can reach: relative residual (f64, torch) of the reference's own per-row system
+    (cymf/wmf.pyx:161-168)  (Y^T Y + wd I + (w - 1) sum_{c in row} y_c y_c^T) x = w sum_{c in row} y_c  for `sample`
+    random rows of the block the session just solved plus its heaviest row; asserts that rows without entries are
+    zero (wmf.pyx:154-156).  Call right after `sess.user_half()` / `sess.item_half()`."""
     torch.manual_seed(seed)
     X_full, R, csr, Y_full = ((sess.dW, sess.Ru, sess.csr_u, sess.dH) if side == "user" else
                               (sess.dH, sess.Ri, sess.csr_i, sess.dW))
