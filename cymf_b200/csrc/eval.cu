@@ -25,8 +25,9 @@ struct EvalArgs {
     const double *log2_table;     // [kmax]: log2(i + 1), evaluated by the host's libm like metrics.pyx:38
     double *per_user;             // [U, nk, 3]  DCG, Recall, MAP  (evaluator.pyx:87-89 `buff`)
     int32_t *order;               // per candidate slot: candidate position by rank, or NULL
-    int32_t U, K, nk, kmax;
+    int32_t U, K, nk, kmax, max_n;
 };
+constexpr int EVAL_TILE_STRIDE = 33;      // doubles per candidate row of a warp's k tile (32 + 1 pad)
 
 __global__ void __launch_bounds__(128) eval_rank_kernel(const EvalArgs a) {
     extern __shared__ double smem[];
@@ -45,11 +46,44 @@ __global__ void __launch_bounds__(128) eval_rank_kernel(const EvalArgs a) {
         for (int k = threadIdx.x; k < a.K; k += blockDim.x) w[k] = a.W[(size_t)u * a.K + k];
         for (int t = threadIdx.x; t < a.kmax; t += blockDim.x) ysorted[t] = 0;
         __syncthreads();
-        for (int t = threadIdx.x; t < n; t += blockDim.x) {                     // evaluator.pyx:113, k ascending
-            const double *h = a.H + (size_t)a.cand_items[c0 + t] * a.K;
-            double acc = 0.0;
-            for (int k = 0; k < a.K; ++k) acc = __dadd_rn(acc, __dmul_rn(__ldg(h + k), w[k]));
-            score[t] = acc;
+        if ((a.K & 1) == 0) {
+            // evaluator.pyx:113 with the k-ascending, separately rounded dot of the oracle -- but the H rows are
+            // fetched cooperatively: per 32-wide k tile a warp reads its 32 candidates' 256-byte row segments with
+            // 128-bit loads (two candidates per instruction, fully coalesced) into a padded shared tile, then every
+            // lane walks ITS candidate's 32 values in order.  (One lane per row straight from global memory touched
+            // 32 different sectors per load instruction.)
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            double *tile = score + a.max_n + (size_t)warp * (32 * EVAL_TILE_STRIDE);
+            for (int base = 0; base < n; base += blockDim.x) {
+                const int t = base + threadIdx.x;
+                const int item = t < n ? a.cand_items[c0 + t] : -1;
+                double acc = 0.0;
+                for (int k0 = 0; k0 < a.K; k0 += 32) {
+#pragma unroll 4
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = 2 * i + (lane >> 4);
+                        const int it = __shfl_sync(0xffffffffu, item, c);
+                        const int k = k0 + (lane & 15) * 2;
+                        double2 v = make_double2(0.0, 0.0);
+                        if (it >= 0 && k < a.K) v = __ldg(reinterpret_cast<const double2 *>(a.H + (size_t)it * a.K + k));
+                        tile[c * EVAL_TILE_STRIDE + (lane & 15) * 2] = v.x;
+                        tile[c * EVAL_TILE_STRIDE + (lane & 15) * 2 + 1] = v.y;
+                    }
+                    __syncwarp();
+                    const int kn = a.K - k0 < 32 ? a.K - k0 : 32;
+                    const double *mine = tile + lane * EVAL_TILE_STRIDE;
+                    for (int kk = 0; kk < kn; ++kk) acc = __dadd_rn(acc, __dmul_rn(mine[kk], w[k0 + kk]));
+                    __syncwarp();
+                }
+                if (t < n) score[t] = acc;
+            }
+        } else {
+            for (int t = threadIdx.x; t < n; t += blockDim.x) {                 // odd K: rows are not 16-byte aligned
+                const double *h = a.H + (size_t)a.cand_items[c0 + t] * a.K;
+                double acc = 0.0;
+                for (int k = 0; k < a.K; ++k) acc = __dadd_rn(acc, __dmul_rn(__ldg(h + k), w[k]));
+                score[t] = acc;
+            }
         }
         __syncthreads();
         for (int t = threadIdx.x; t < n; t += blockDim.x) {
@@ -136,8 +170,9 @@ extern "C" int cymf_eval_rank_dev(const double *W, const double *H, int32_t U, i
                                   int32_t kmax, double *per_user, int32_t *order, void *stream) {
     CYMF_REQUIRE(W && H && test_indptr && cand_ptr && cand_items && ks && log2_table && per_user, "null pointer");
     CYMF_REQUIRE(U > 0 && K > 0 && nk > 0 && nk <= 32 && kmax > 0 && kmax <= 128, "bad shape (1..32 cut-offs, k <= 128)");
-    EvalArgs a{W, H, test_indptr, cand_ptr, cand_items, ks, log2_table, per_user, order, U, K, nk, kmax};
-    const size_t smem = sizeof(double) * ((size_t)K + (size_t)(max_candidates > 0 ? max_candidates : 1));
+    const int32_t max_n = max_candidates > 0 ? max_candidates : 1;
+    EvalArgs a{W, H, test_indptr, cand_ptr, cand_items, ks, log2_table, per_user, order, U, K, nk, kmax, max_n};
+    const size_t smem = sizeof(double) * ((size_t)K + (size_t)max_n + (size_t)4 * 32 * EVAL_TILE_STRIDE);
     if (smem > 200 * 1024) { set_error("evaluator: %d candidates for one user exceed shared memory", max_candidates); return CYMF_EUNSUPPORTED; }
     if (smem > 48 * 1024)
         CYMF_CUDA(cudaFuncSetAttribute(eval_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
