@@ -139,18 +139,25 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const uint32_t 
     hist[(int64_t)threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];
 }
 
+// One tile: stable ranks inside each warp round from eight ballots (one per digit bit; cheaper than match.any),
+// per-warp digit counters, exclusive prefixes over warps and over digits, then the tile is written to shared memory in
+// digit-sorted order and leaves as contiguous runs -- every digit's elements of the tile are consecutive in the
+// output, so consecutive threads store consecutive addresses.
 __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const uint32_t *__restrict__ keys,
                                                                      const uint32_t *__restrict__ vals, int64_t n,
                                                                      int shift, const uint32_t *__restrict__ offsets,
                                                                      int64_t tiles, uint32_t *__restrict__ out_keys,
                                                                      uint32_t *__restrict__ out_vals) {
     __shared__ uint32_t cnt[SORT_WARPS][256];
-    __shared__ uint32_t gbase[256];
+    __shared__ uint32_t gbase[256], dstart[256];
+    __shared__ uint32_t skey[SORT_TILE], sval[SORT_TILE];
+    __shared__ uint64_t scan_tmp[33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int t = threadIdx.x; t < SORT_WARPS * 256; t += SORT_THREADS) (&cnt[0][0])[t] = 0;
     gbase[threadIdx.x] = offsets[(int64_t)threadIdx.x * tiles + blockIdx.x];
     __syncthreads();
-    const int64_t wbase = (int64_t)blockIdx.x * SORT_TILE + (int64_t)warp * SORT_WARP_SPAN;
+    const int64_t tile_base = (int64_t)blockIdx.x * SORT_TILE;
+    const int64_t wbase = tile_base + (int64_t)warp * SORT_WARP_SPAN;
     uint32_t k[SORT_ROUNDS], v[SORT_ROUNDS];
     uint16_t off[SORT_ROUNDS];
     const unsigned lt = (1u << lane) - 1u;
@@ -160,31 +167,49 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const uint32
         const bool valid = idx < n;
         k[r] = valid ? keys[idx] : 0u;
         v[r] = (valid && vals) ? vals[idx] : 0u;
-        const uint32_t d = valid ? ((k[r] >> shift) & 255u) : 256u;          // 256 = "no element"
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
+        const uint32_t d = (k[r] >> shift) & 255u;
+        unsigned peers = __ballot_sync(0xffffffffu, valid);                  // lanes holding the same digit as mine
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+            peers &= ((d >> b) & 1u) ? bal : ~bal;
+        }
         uint32_t before = 0;
-        if (lane == leader && valid) { before = cnt[warp][d]; cnt[warp][d] = before + __popc(peers); }
-        before = __shfl_sync(0xffffffffu, before, leader);
+        if (valid) {
+            const int leader = __ffs(peers) - 1;
+            if (lane == leader) { before = cnt[warp][d]; cnt[warp][d] = before + __popc(peers); }
+            before = __shfl_sync(peers, before, leader);
+        }
         off[r] = (uint16_t)(before + __popc(peers & lt));                    // rank inside the warp's span, stable
         __syncwarp();
     }
     __syncthreads();
-    {   // exclusive prefix over the warps for digit = threadIdx.x
-        uint32_t acc = 0;
+    uint32_t total = 0;
+    {   // digit = threadIdx.x: exclusive prefix over the warps, then over the digits
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; ++w) { const uint32_t t = cnt[w][threadIdx.x]; cnt[w][threadIdx.x] = acc; acc += t; }
+        for (int w = 0; w < SORT_WARPS; ++w) { const uint32_t t = cnt[w][threadIdx.x]; cnt[w][threadIdx.x] = total; total += t; }
     }
+    uint64_t tile_total;
+    dstart[threadIdx.x] = (uint32_t)block_exclusive((uint64_t)total, scan_tmp, &tile_total);
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; ++r) {
         const int64_t idx = wbase + r * 32 + lane;
         if (idx < n) {
             const uint32_t d = (k[r] >> shift) & 255u;
-            const int64_t pos = (int64_t)gbase[d] + cnt[warp][d] + off[r];
-            out_keys[pos] = k[r];
-            if (out_vals) out_vals[pos] = v[r];
+            const uint32_t lp = dstart[d] + cnt[warp][d] + off[r];
+            skey[lp] = k[r];
+            sval[lp] = v[r];
         }
+    }
+    __syncthreads();
+    const int n_tile = (int)(n - tile_base < SORT_TILE ? n - tile_base : SORT_TILE);
+    for (int s = threadIdx.x; s < n_tile; s += SORT_THREADS) {
+        const uint32_t key = skey[s];
+        const uint32_t d = (key >> shift) & 255u;
+        const int64_t pos = (int64_t)gbase[d] + (s - dstart[d]);
+        out_keys[pos] = key;
+        if (out_vals) out_vals[pos] = sval[s];
     }
 }
 
@@ -449,34 +474,68 @@ __global__ void cooc_heads_kernel(const CoocView v, const uint32_t *__restrict__
         head[q] = h;
     }
 }
-// One thread per cell: the cell's slots are contiguous and in corpus order; 1.0 / distance is added one by one
-// (glove.pyx:221) -- f64 addition is not associative, so the order IS the result.  The inner loop touches only the
-// two streamed arrays (ids, head) and a shared table of reciprocals: the chain of dependent additions of the most
-// frequent cell (~1 % of all updates for a Zipf corpus) is what bounds the kernel.
-__global__ void cooc_sum_kernel(const CoocView v, const uint32_t *__restrict__ ids, const uint32_t *__restrict__ head,
-                                const int64_t *__restrict__ cell_of, const int64_t *__restrict__ n_valid_ptr,
-                                int64_t capacity, int32_t *__restrict__ rows, int32_t *__restrict__ cols,
-                                double *__restrict__ vals) {
+// start[c] = first sorted slot of cell c (cells are numbered by the scan of the head flags); start[nnz] = n_valid
+__global__ void cooc_cell_starts_kernel(const uint32_t *__restrict__ head, const int64_t *__restrict__ cell_of,
+                                        int64_t n_pairs, const int64_t *__restrict__ n_valid, uint32_t *__restrict__ start) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_pairs; q += (int64_t)gridDim.x * blockDim.x)
+        if (head[q]) start[cell_of[q]] = (uint32_t)q;
+    if (blockIdx.x == 0 && threadIdx.x == 0) start[cell_of[n_pairs]] = (uint32_t)*n_valid;
+}
+// A cell's slots are contiguous and in corpus order; 1.0 / distance is added one by one (glove.pyx:221) -- f64 addition
+// is not associative, so the order IS the result.  One thread per cell for the short ones (3.5 slots on average);
+// cells of >= 64 slots go to a work list for cooc_sum_long_kernel.
+constexpr int COOC_LONG = 64;
+__global__ void cooc_sum_short_kernel(const CoocView v, const uint32_t *__restrict__ ids,
+                                      const uint32_t *__restrict__ start, const int64_t *__restrict__ nnz_ptr,
+                                      int64_t capacity, int32_t *__restrict__ rows, int32_t *__restrict__ cols,
+                                      double *__restrict__ vals, uint32_t *__restrict__ work,
+                                      unsigned long long *__restrict__ n_work) {
     extern __shared__ double recip[];                       // recip[s] = 1.0 / (window - s), s = slot % window
     for (int s = threadIdx.x; s < v.window; s += blockDim.x) recip[s] = __ddiv_rn(1.0, (double)(v.window - s));
     __syncthreads();
-    const int64_t n_valid = *n_valid_ptr;
+    const int64_t cells = *nnz_ptr < capacity ? *nnz_ptr : capacity;
     const uint32_t window = (uint32_t)v.window;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_valid; q += (int64_t)gridDim.x * blockDim.x) {
-        if (!head[q]) continue;
-        const int64_t cell = cell_of[q];
-        if (cell >= capacity) continue;
-        int32_t r, c, d;
-        v.decode(ids[q], &r, &c, &d);
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t lo = start[c], hi = start[c + 1];
+        int32_t r, cc, d;
+        v.decode(ids[lo], &r, &cc, &d);
+        rows[c] = r;
+        cols[c] = cc;
+        if (hi - lo >= (uint32_t)COOC_LONG) { work[atomicAdd(n_work, 1ull)] = (uint32_t)c; continue; }
         double sum = 0.0;
-        int64_t t = q;
-        do {
-            sum = __dadd_rn(sum, recip[ids[t] % window]);
-            ++t;
-        } while (t < n_valid && !head[t]);
-        rows[cell] = r;
-        cols[cell] = c;
-        vals[cell] = sum;
+        for (uint32_t t = lo; t < hi; ++t) sum = __dadd_rn(sum, recip[ids[t] % window]);
+        vals[c] = sum;
+    }
+}
+// One warp per long cell (the most frequent pair of a Zipf corpus holds ~1 % of all updates): 32 addends are fetched
+// with one coalesced load and handed to the running sum in slot order through shuffles, so the serial chain carries
+// only the additions themselves.  Slots past the end contribute +0.0, which leaves any sum unchanged.
+__global__ void __launch_bounds__(128) cooc_sum_long_kernel(const CoocView v, const uint32_t *__restrict__ ids,
+                                                            const uint32_t *__restrict__ start,
+                                                            const uint32_t *__restrict__ work,
+                                                            const unsigned long long *__restrict__ n_work,
+                                                            double *__restrict__ vals) {
+    extern __shared__ double recip[];
+    for (int s = threadIdx.x; s < v.window; s += blockDim.x) recip[s] = __ddiv_rn(1.0, (double)(v.window - s));
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t window = (uint32_t)v.window;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n = (int64_t)*n_work;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += warps) {
+        const uint32_t c = work[w];
+        const uint32_t lo = start[c], hi = start[c + 1];
+        double sum = 0.0;
+        uint32_t t = lo + lane;
+        double next = t < hi ? recip[ids[t] % window] : 0.0;
+        for (uint32_t base = lo; base < hi; base += 32) {
+            const double a = next;
+            t = base + 32 + lane;
+            next = (base + 32 < hi && t < hi) ? recip[ids[t] % window] : 0.0;        // next chunk already in flight
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum = __dadd_rn(sum, __shfl_sync(0xffffffffu, a, j));
+        }
+        if (lane == 0) vals[c] = sum;
     }
 }
 
@@ -484,7 +543,7 @@ __global__ void cooc_sum_kernel(const CoocView v, const uint32_t *__restrict__ i
 
 extern "C" int64_t cymf_cooc_workspace_bytes(int64_t n_tokens, int32_t window) {
     const int64_t P = n_tokens * (int64_t)window;
-    return (int64_t)(3 * align256((size_t)P * 4) + align256((size_t)(P + 1) * 8) + sort_workspace_bytes(P) +
+    return (int64_t)(3 * align256((size_t)(P + 1) * 4) + align256((size_t)(P + 1) * 8) + sort_workspace_bytes(P) +
                      (size_t)cymf_scan_workspace_bytes(P) + 256);
 }
 
@@ -501,14 +560,15 @@ extern "C" int cymf_cooc_count_dev(const int32_t *tokens, const int32_t *pos_in_
     if (P == 0) { CYMF_CUDA(cudaMemsetAsync(nnz_out, 0, 8, st)); return 0; }
     CYMF_REQUIRE(tokens && pos_in_line && rows && cols && vals, "null pointer");
     char *ws = (char *)workspace;
-    uint32_t *keys = (uint32_t *)ws; ws += align256((size_t)P * 4);
-    uint32_t *ids = (uint32_t *)ws; ws += align256((size_t)P * 4);
-    uint32_t *head = (uint32_t *)ws; ws += align256((size_t)P * 4);
+    uint32_t *keys = (uint32_t *)ws; ws += align256((size_t)(P + 1) * 4);      // sort keys, then the cells' first slots
+    uint32_t *ids = (uint32_t *)ws; ws += align256((size_t)(P + 1) * 4);
+    uint32_t *head = (uint32_t *)ws; ws += align256((size_t)(P + 1) * 4);      // head flags, then the long-cell work list
     int64_t *cell_of = (int64_t *)ws; ws += align256((size_t)(P + 1) * 8);
     void *sort_ws = ws; ws += sort_workspace_bytes(P);
     void *scan_ws = ws; ws += (size_t)cymf_scan_workspace_bytes(P);
     int64_t *n_valid = (int64_t *)ws;
-    CYMF_CUDA(cudaMemsetAsync(n_valid, 0, 8, st));
+    unsigned long long *n_work = (unsigned long long *)(ws + 8);
+    CYMF_CUDA(cudaMemsetAsync(n_valid, 0, 16, st));
     const CoocView v{tokens, pos_in_line, P, window, vocab};
     const int bits = bits_for((int64_t)vocab + 1);
     cooc_col_keys_kernel<<<flat_grid(P), 256, 0, st>>>(v, keys, ids);
@@ -521,7 +581,13 @@ extern "C" int cymf_cooc_count_dev(const int32_t *tokens, const int32_t *pos_in_
     CYMF_LAUNCHED();
     CYMF_TRY((exclusive_scan<uint32_t, int64_t>(head, cell_of, P, 1, (uint64_t *)scan_ws, st)));
     CYMF_CUDA(cudaMemcpyAsync(nnz_out, cell_of + P, 8, cudaMemcpyDeviceToDevice, st));
-    cooc_sum_kernel<<<flat_grid(P), 256, (size_t)window * 8, st>>>(v, ids, head, cell_of, n_valid, capacity, rows, cols, vals);
+    uint32_t *start = keys, *work = head;
+    cooc_cell_starts_kernel<<<flat_grid(P), 256, 0, st>>>(head, cell_of, P, n_valid, start);
+    CYMF_LAUNCHED();
+    cooc_sum_short_kernel<<<flat_grid(P), 256, (size_t)window * 8, st>>>(v, ids, start, nnz_out, capacity, rows, cols, vals,
+                                                                      work, n_work);
+    CYMF_LAUNCHED();
+    cooc_sum_long_kernel<<<(unsigned)sm_count() * 8, 128, (size_t)window * 8, st>>>(v, ids, start, work, n_work, vals);
     CYMF_LAUNCHED();
     return 0;
 }
