@@ -76,3 +76,60 @@ def test_no_cpu_fallback():
     import cymf_b200 as cymf
     with pytest.raises(_lib.CymfError, match="no CPU fallback"):
         cymf.BPR(4, optimizer="sgd").fit(np.eye(4), num_epochs=1, verbose=False)
+
+
+def test_host_rng_wide_ranges_match_libstdcxx_vectors():
+    """cymf_rng_fill_below64: the raw-word (n = 2^32) and upscaling (n > 2^32) branches of libstdc++'s
+    uniform_int_distribution<long>, which RelMF's replay needs for U*I cells (cymf/relmf.pyx:127)."""
+    g = golden("rng64.npz")
+    for n in (3703857792, 4294967296, 4294967297, 5000000000, 10000000000000):
+        want = g[f"below_{n}_seed1234"]
+        assert np.array_equal(_lib.HostRng(1234).below64(n, want.shape[0]), want), n
+    r = _lib.HostRng(1234)                      # narrow ranges go through the same 32-bit path as below()
+    assert np.array_equal(r.below64(1682, 64), golden("rng.npz")["below_1682_seed1234"])
+
+
+def test_relmf_contract_and_propensities():
+    import cymf_b200 as cymf
+    from cymf_b200.relmf import item_propensities
+    from scipy import sparse
+    with pytest.raises(Exception, match="rmsprop is invalid."):
+        cymf.RelMF(optimizer="rmsprop")                                       # relmf.pyx:65-66
+    m = cymf.RelMF()
+    assert (m.num_components, m.clip_value, m.learning_rate, m.optimizer, m.weight_decay) == (20, 0.1, 0.001, "adam", 0.01)
+    assert m.W is None and m.H is None
+    with pytest.raises(ValueError):
+        m.fit(None)
+    rng = np.random.default_rng(3)
+    A = (rng.random((50, 40)) < 0.2) * rng.integers(1, 6, (50, 40)) / 5.0
+    A[:, 7] = 0                                                                # an item nobody has: floor 1e-5
+    want = np.maximum(A.mean(axis=0) / A.mean(axis=0).max(), 1e-5) ** 0.5     # relmf.pyx:90 on the dense matrix
+    assert np.array_equal(item_propensities(sparse.csr_matrix(A)), want)
+
+
+def test_read_text_without_vocabulary_needs_no_gpu(tmp_path):
+    """min_count above every word count: the reference returns an empty 0 x 0 matrix and an empty map."""
+    import cymf_b200 as cymf
+    f = tmp_path / "tiny.txt"
+    f.write_text("a b c a b")
+    X, i2w = cymf.glove.read_text(str(f), 5, 3)
+    assert X.shape == (0, 0) and X.nnz == 0 and i2w == {}
+    with pytest.raises(KeyError):                                              # glove.pyx:199-209: "c<eos>d" hides c and d
+        g = tmp_path / "two_lines.txt"
+        g.write_text("a b c\nd a b")
+        cymf.glove.read_text(str(g), 1, 2)
+
+
+def test_wmf_and_relmf_argument_validation():
+    import cymf_b200 as cymf
+    with pytest.raises(ValueError):
+        cymf.WMF(prep="somewhere")
+    with pytest.raises(ValueError):
+        cymf.WMF(129)
+    with pytest.raises(ValueError):
+        cymf.RelMF(mode="serial")
+    L = _lib.lib()
+    assert L.cymf_sort_pairs_dev(None, None, 5, 8, None, None) == -1 and b"bad argument" in L.cymf_last_error()
+    assert L.cymf_cooc_count_dev(None, None, 1 << 30, 10, 8, None, None, None, 0, None, None, None) == -1
+    assert L.cymf_als_heavy_workspace_doubles(3, 128, 128) == 3 * (128 * 128 + 128)
+    assert L.cymf_cooc_workspace_bytes(1000, 10) > 10000 * 20
