@@ -191,6 +191,10 @@ __device__ __forceinline__ void warp_allsum4(T &d0, T &d1, T &d2, T &d3, int lan
 }
 constexpr int CG_VEC = 128;           // capacity of the shared K-vectors (ld <= 128)
 
+// element offset of row r of an [n, ld] matrix; r >= 0, so the product is one unsigned wide multiply (IMAD.WIDE.U32)
+// instead of the sign-extending 64-bit multiply chain (6 -> 3 instructions per gathered row in the CG loops)
+__device__ __forceinline__ size_t yrow_off(int32_t r, int ld) { return (size_t)((uint64_t)(uint32_t)r * (uint32_t)ld); }
+
 // acc + d0 y0 + d1 y1 + d2 y2 + d3 y3 as one chain of four fused multiply-adds (the CG kernel is issue-bound on
 // short rows -- 73 % issue-active, profiles/r1_als_cg_c5_scale03_ncu_full.txt -- and the pairwise form cost six
 // instructions per element instead of four)
@@ -332,6 +336,21 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
         out = o_;                                                                                  \
     }
 
+#define CYMF_STREAM_LOAD(v0, v1, v2, v3)                                                            \
+                if (lane_on) {                                                                     \
+                    ldg_vec<VW>(Yq + yrow_off(__ldg(idx + i), ld), v0);                            \
+                    ldg_vec<VW>(Yq + yrow_off(__ldg(idx + i + NW), ld), v1);                       \
+                    ldg_vec<VW>(Yq + yrow_off(__ldg(idx + i + 2 * NW), ld), v2);                   \
+                    ldg_vec<VW>(Yq + yrow_off(__ldg(idx + i + 3 * NW), ld), v3);                   \
+                }
+#define CYMF_STREAM_GROUP(v0, v1, v2, v3)                                                           \
+                {                                                                                  \
+                    T d0 = dot_slice<T, VW>(v0, ps), d1 = dot_slice<T, VW>(v1, ps),                \
+                      d2 = dot_slice<T, VW>(v2, ps), d3 = dot_slice<T, VW>(v3, ps);                \
+                    warp_allsum4(d0, d1, d2, d3, lane);                                            \
+                    axpy4<T, VW>(acc, d0, v0, d1, v1, d2, v2, d3, v3);                             \
+                }
+
 // A v for the vector in p_s -> element `tid` of the result in `out` (0 for tid >= ld).  One barrier inside.
 // The warp's items are warp, warp+NW, ...; four at a time share one reduction butterfly.
 #define CYMF_APPLY(out)                                                                            \
@@ -354,31 +373,23 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
             axpy4<T, VW>(acc, d0, y0, d1, y1, d2, y2, d3, y3);                                     \
         }                                                                                          \
         if (i < ns) { CYMF_MIXED_GROUP(); i += 4 * NW; }        /* the group that straddles the staging limit */ \
-        if (i + 3 * NW < nnz) {                                 /* streamed groups, next group's gathers in flight */ \
-            T n0[VW], n1[VW], n2[VW], n3[VW];                                                      \
-            _Pragma("unroll") for (int e = 0; e < VW; ++e) { n0[e] = n1[e] = n2[e] = n3[e] = T(0); } \
-            if (lane_on) {                                                                         \
-                ldg_vec<VW>(Yq + (size_t)__ldg(idx + i) * ld, n0);                                 \
-                ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + NW) * ld, n1);                            \
-                ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + 2 * NW) * ld, n2);                        \
-                ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + 3 * NW) * ld, n3);                        \
+        if (i + 3 * NW < nnz) {                /* streamed groups: two register sets take turns, the other one's gathers in flight */ \
+            T a0[VW], a1[VW], a2[VW], a3[VW], b0[VW], b1[VW], b2[VW], b3[VW];                      \
+            _Pragma("unroll") for (int e = 0; e < VW; ++e) {                                       \
+                a0[e] = a1[e] = a2[e] = a3[e] = T(0); b0[e] = b1[e] = b2[e] = b3[e] = T(0);        \
             }                                                                                      \
+            CYMF_STREAM_LOAD(a0, a1, a2, a3)                                                       \
             for (;;) {                                                                             \
-                T y0[VW], y1[VW], y2[VW], y3[VW];                                                  \
-                _Pragma("unroll") for (int e = 0; e < VW; ++e) { y0[e] = n0[e]; y1[e] = n1[e]; y2[e] = n2[e]; y3[e] = n3[e]; } \
                 i += 4 * NW;                                                                       \
-                const bool more = i + 3 * NW < nnz;                                                \
-                if (more && lane_on) {                                                             \
-                    ldg_vec<VW>(Yq + (size_t)__ldg(idx + i) * ld, n0);                             \
-                    ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + NW) * ld, n1);                        \
-                    ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + 2 * NW) * ld, n2);                    \
-                    ldg_vec<VW>(Yq + (size_t)__ldg(idx + i + 3 * NW) * ld, n3);                    \
-                }                                                                                  \
-                T d0 = dot_slice<T, VW>(y0, ps), d1 = dot_slice<T, VW>(y1, ps),                    \
-                  d2 = dot_slice<T, VW>(y2, ps), d3 = dot_slice<T, VW>(y3, ps);                    \
-                warp_allsum4(d0, d1, d2, d3, lane);                                                \
-                axpy4<T, VW>(acc, d0, y0, d1, y1, d2, y2, d3, y3);                                 \
-                if (!more) break;                                                                  \
+                const bool more_b = i + 3 * NW < nnz;                                              \
+                if (more_b) { CYMF_STREAM_LOAD(b0, b1, b2, b3) }                                   \
+                CYMF_STREAM_GROUP(a0, a1, a2, a3)                                                  \
+                if (!more_b) break;                                                                \
+                i += 4 * NW;                                                                       \
+                const bool more_a = i + 3 * NW < nnz;                                              \
+                if (more_a) { CYMF_STREAM_LOAD(a0, a1, a2, a3) }                                   \
+                CYMF_STREAM_GROUP(b0, b1, b2, b3)                                                  \
+                if (!more_a) break;                                                                \
             }                                                                                      \
         }                                                                                          \
         for (; i < nnz; i += 4 * NW) { CYMF_MIXED_GROUP(); }    /* tail */                         \
@@ -394,13 +405,13 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
             if (lane_on) {                                                                         \
                 const int i1 = i + NW, i2 = i + 2 * NW, i3 = i + 3 * NW;                           \
                 if (i < ns) ld_vec<VW>(Ys + i * ld + kq, y0);                                      \
-                else ldg_vec<VW>(Yq + (size_t)__ldg(idx + i) * ld, y0);                            \
+                else ldg_vec<VW>(Yq + yrow_off(__ldg(idx + i), ld), y0);                            \
                 if (i1 < ns) ld_vec<VW>(Ys + i1 * ld + kq, y1);                                    \
-                else if (i1 < nnz) ldg_vec<VW>(Yq + (size_t)__ldg(idx + i1) * ld, y1);             \
+                else if (i1 < nnz) ldg_vec<VW>(Yq + yrow_off(__ldg(idx + i1), ld), y1);             \
                 if (i2 < ns) ld_vec<VW>(Ys + i2 * ld + kq, y2);                                    \
-                else if (i2 < nnz) ldg_vec<VW>(Yq + (size_t)__ldg(idx + i2) * ld, y2);             \
+                else if (i2 < nnz) ldg_vec<VW>(Yq + yrow_off(__ldg(idx + i2), ld), y2);             \
                 if (i3 < ns) ld_vec<VW>(Ys + i3 * ld + kq, y3);                                    \
-                else if (i3 < nnz) ldg_vec<VW>(Yq + (size_t)__ldg(idx + i3) * ld, y3);             \
+                else if (i3 < nnz) ldg_vec<VW>(Yq + yrow_off(__ldg(idx + i3), ld), y3);             \
             }                                                                                      \
             T d0 = dot_slice<T, VW>(y0, ps), d1 = dot_slice<T, VW>(y1, ps), d2 = dot_slice<T, VW>(y2, ps),      \
               d3 = dot_slice<T, VW>(y3, ps);                                                       \
@@ -442,33 +453,41 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
             for (int e = 0; e < VW; ++e) { bacc[e] = acc[e] = ps[e] = T(0); c0[e] = c1[e] = c2[e] = c3[e] = T(0); }
             if (lane_on) ld_vec<VW>(p_s + kq, ps);
 #define CYMF_GATHER4(at, v0, v1, v2, v3)                                                           \
+            if ((at) + 3 * NW >= nnz) {                      /* partial (or empty) group: clear the set first */ \
+                _Pragma("unroll") for (int e = 0; e < VW; ++e) v0[e] = v1[e] = v2[e] = v3[e] = T(0); \
+            }                                                                                      \
             if (lane_on) {                                                                         \
-                if ((at) < nnz) ldg_vec<VW>(Yq + (size_t)__ldg(idx + (at)) * ld, v0);              \
-                if ((at) + NW < nnz) ldg_vec<VW>(Yq + (size_t)__ldg(idx + (at) + NW) * ld, v1);    \
-                if ((at) + 2 * NW < nnz) ldg_vec<VW>(Yq + (size_t)__ldg(idx + (at) + 2 * NW) * ld, v2); \
-                if ((at) + 3 * NW < nnz) ldg_vec<VW>(Yq + (size_t)__ldg(idx + (at) + 3 * NW) * ld, v3); \
+                if ((at) < nnz) ldg_vec<VW>(Yq + yrow_off(__ldg(idx + (at)), ld), v0);              \
+                if ((at) + NW < nnz) ldg_vec<VW>(Yq + yrow_off(__ldg(idx + (at) + NW), ld), v1);    \
+                if ((at) + 2 * NW < nnz) ldg_vec<VW>(Yq + yrow_off(__ldg(idx + (at) + 2 * NW), ld), v2); \
+                if ((at) + 3 * NW < nnz) ldg_vec<VW>(Yq + yrow_off(__ldg(idx + (at) + 3 * NW), ld), v3); \
             }
+#define CYMF_FIRST_GROUP(at, v0, v1, v2, v3)                                                       \
+            {                                                                                      \
+                if (lane_on) {                                                                     \
+                    if ((at) < ns) st_vec<VW>(Ys + (at) * ld + kq, v0);                            \
+                    if ((at) + NW < ns) st_vec<VW>(Ys + ((at) + NW) * ld + kq, v1);                \
+                    if ((at) + 2 * NW < ns) st_vec<VW>(Ys + ((at) + 2 * NW) * ld + kq, v2);        \
+                    if ((at) + 3 * NW < ns) st_vec<VW>(Ys + ((at) + 3 * NW) * ld + kq, v3);        \
+                }                                                                                  \
+                _Pragma("unroll") for (int e = 0; e < VW; ++e) bacc[e] += (v0[e] + v1[e]) + (v2[e] + v3[e]); \
+                T d0 = dot_slice<T, VW>(v0, ps), d1 = dot_slice<T, VW>(v1, ps), d2 = dot_slice<T, VW>(v2, ps), \
+                  d3 = dot_slice<T, VW>(v3, ps);                                                   \
+                warp_allsum4(d0, d1, d2, d3, lane);                                                \
+                axpy4<T, VW>(acc, d0, v0, d1, v1, d2, v2, d3, v3);                                 \
+            }
+            T n0[VW], n1[VW], n2[VW], n3[VW];
+#pragma unroll
+            for (int e = 0; e < VW; ++e) n0[e] = n1[e] = n2[e] = n3[e] = T(0);
             CYMF_GATHER4(warp, c0, c1, c2, c3)
-            for (int i = warp; i < nnz; i += 4 * NW) {
-                T n0[VW], n1[VW], n2[VW], n3[VW];
-#pragma unroll
-                for (int e = 0; e < VW; ++e) n0[e] = n1[e] = n2[e] = n3[e] = T(0);
+            for (int i = warp; i < nnz; i += 8 * NW) {           // two register sets take turns (no copies)
                 CYMF_GATHER4(i + 4 * NW, n0, n1, n2, n3)
-                if (lane_on) {
-                    if (i < ns) st_vec<VW>(Ys + i * ld + kq, c0);
-                    if (i + NW < ns) st_vec<VW>(Ys + (i + NW) * ld + kq, c1);
-                    if (i + 2 * NW < ns) st_vec<VW>(Ys + (i + 2 * NW) * ld + kq, c2);
-                    if (i + 3 * NW < ns) st_vec<VW>(Ys + (i + 3 * NW) * ld + kq, c3);
-                }
-#pragma unroll
-                for (int e = 0; e < VW; ++e) bacc[e] += (c0[e] + c1[e]) + (c2[e] + c3[e]);
-                T d0 = dot_slice<T, VW>(c0, ps), d1 = dot_slice<T, VW>(c1, ps), d2 = dot_slice<T, VW>(c2, ps),
-                  d3 = dot_slice<T, VW>(c3, ps);
-                warp_allsum4(d0, d1, d2, d3, lane);
-                axpy4<T, VW>(acc, d0, c0, d1, c1, d2, c2, d3, c3);
-#pragma unroll
-                for (int e = 0; e < VW; ++e) { c0[e] = n0[e]; c1[e] = n1[e]; c2[e] = n2[e]; c3[e] = n3[e]; }
+                CYMF_FIRST_GROUP(i, c0, c1, c2, c3)
+                if (i + 4 * NW >= nnz) break;
+                CYMF_GATHER4(i + 8 * NW, c0, c1, c2, c3)
+                CYMF_FIRST_GROUP(i + 4 * NW, n0, n1, n2, n3)
             }
+#undef CYMF_FIRST_GROUP
 #undef CYMF_GATHER4
             if (lane_on) st_vec<VW>(part + warp * CG_VEC + kq, bacc);
         }
@@ -540,6 +559,8 @@ __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
             if (stalled) atomicAdd(a.stats + 1, 1ull);
         }
 #undef CYMF_APPLY
+#undef CYMF_STREAM_LOAD
+#undef CYMF_STREAM_GROUP
 #undef CYMF_BLOCK_SUM
 #undef CYMF_BLOCK_SUM2
 #undef CYMF_MIXED_GROUP
