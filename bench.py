@@ -119,12 +119,15 @@ def time_bpr_device(train, users, positives, K, optimizer, steps, warmup, dtype=
         s.epoch(lr, wd)
     torch.cuda.synchronize()
     a0 = s.applied()
+    from cymf_b200 import _lib
+    l0 = _lib.launch_count()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     evs[0].record()
     for t in range(steps):
         s.epoch(lr, wd)
         evs[t + 1].record()
     torch.cuda.synchronize()
+    s.timed_launches = _lib.launch_count() - l0               # kernels of this library inside the timed region
     per_step = [evs[t].elapsed_time(evs[t + 1]) * 1e-3 for t in range(steps)]
     return sum(per_step), s.applied() - a0, s, per_step
 
@@ -439,7 +442,7 @@ def main():
     secs, applied, sess, per_step = time_bpr_device(train, users, positives, K_MAIN, "sgd", args.steps, args.warmup)
     sync_all()
     clocks = sampler.stop()
-    launches = _lib.launch_count() - launches0 - args.warmup - 2     # minus warm-up epochs and the 2 pack kernels
+    launches = sess.timed_launches
     stats = torch.tensor([secs, float(applied)], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = stats.clone()

@@ -50,6 +50,8 @@ SIGNATURES = {
     "cymf_fill_dev": (C.c_int, [_p, C.c_int, _i64, _f64, _p]),
     "cymf_bpr_hogwild_epoch_dev": (C.c_int, [C.POINTER(Factors), C.c_int, C.c_int, C.c_int, _p, _p, _i64, _p, _p,
                                              _i32, _i32, _i32, _i32, _f64, _f64, _u64, _u32, _i64, _p, _p]),
+    "cymf_bpr_hogwild_range_dev": (C.c_int, [C.POINTER(Factors), C.c_int, C.c_int, C.c_int, _p, _p, _i64, _p, _p,
+                                             _i32, _i32, _i32, _i32, _f64, _f64, _u64, _u32, _i64, _p, _i64, _p]),
     "cymf_bpr_negatives_host": (C.c_int, [_u64, _u32, _i64, _i64, _u32, _p]),
     "cymf_bpr_replay_epoch_dev":(C.c_int, [C.POINTER(Factors), C.c_int, _p, _p, _p, _i64, _p, _p,
                                             _i32, _i32, _i32, _i32, _f64, _f64, _p, _p]),

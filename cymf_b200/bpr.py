@@ -135,12 +135,35 @@ class BprSession(object):
         self.ld = ld = _lib.ld_for(K)
         U, I = self.U, self.I
         with torch.cuda.device(dev):
-            self.d_users = torch.from_numpy(np.ascontiguousarray(users, np.int32)).to(dev, non_blocking=True)
-            self.d_pos = torch.from_numpy(np.ascontiguousarray(positives, np.int32)).to(dev, non_blocking=True)
+            # Upload order = order of first use: factors and CSR first, then the pair list in ranges on a copy
+            # stream, so that the first epoch starts on range 0 while the later ranges are still crossing PCIe
+            # (the kernel needs every factor row from its first triplet on, but only the pairs it has reached).
             self.d_indptr = torch.from_numpy(X.indptr.astype(np.int64)).to(dev, non_blocking=True)
             self.d_indices = torch.from_numpy(np.ascontiguousarray(X.indices, np.int32)).to(dev, non_blocking=True)
             self.dW = _lib.upload_factor(W, self.dtype, dev)
             self.dH = _lib.upload_factor(H, self.dtype, dev)
+            src_u = torch.from_numpy(np.ascontiguousarray(users, np.int32))
+            src_p = torch.from_numpy(np.ascontiguousarray(positives, np.int32))
+            self.d_users = torch.empty(N, dtype=torch.int32, device=dev)
+            self.d_pos = torch.empty(N, dtype=torch.int32, device=dev)
+            self._ranges = []
+            n_ranges = 4 if (N >= (1 << 22) and mode != "replay") else 1
+            copy_stream = torch.cuda.Stream(device=dev) if n_ranges > 1 else torch.cuda.current_stream()
+            bounds = [N * q // n_ranges for q in range(n_ranges + 1)]
+            if n_ranges > 1:
+                # the buffers were just handed out by the caching allocator in main-stream order: earlier main-stream
+                # work may still be using their memory, so the copy stream starts behind it (which is also the
+                # upload order wanted: factors and CSR first)
+                copy_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(copy_stream):
+                for a, b in zip(bounds[:-1], bounds[1:]):
+                    self.d_users[a:b].copy_(src_u[a:b], non_blocking=True)
+                    self.d_pos[a:b].copy_(src_p[a:b], non_blocking=True)
+                    if n_ranges > 1:
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                        self._ranges.append((a, b, ev))
+            self._keep_src = (src_u, src_p)                      # alive until the copies have been consumed
             self.state = []
             if opt == _lib.ADAGRAD:
                 self.state = [torch.ones((U, ld), dtype=tdt, device=dev), torch.ones((I, ld), dtype=tdt, device=dev)]
@@ -175,11 +198,19 @@ class BprSession(object):
                     learning_rate, weight_decay, _lib.ptr(self.d_applied), stream))
                 self._keep = neg                                 # alive until the kernel has consumed it
             else:
-                _lib.check(L.cymf_bpr_hogwild_epoch_dev(
-                    C.byref(f), self.dtype, self.opt, self.scatter, _lib.ptr(self.d_users), _lib.ptr(self.d_pos),
-                    self.N, _lib.ptr(self.d_indptr), _lib.ptr(self.d_indices), self.U, self.I, self.K, self.ld,
-                    learning_rate, weight_decay, self.seed, self.epochs_done, self.inflight,
-                    _lib.ptr(self.d_applied), stream))
+                # the first epoch follows the pair ranges as they arrive; the negatives are keyed by the pair's
+                # position in the epoch, so the result does not depend on how the epoch is cut
+                ranges = self._ranges if (self.epochs_done == 0 and self._ranges) else [(0, self.N, None)]
+                for a, b, ev in ranges:
+                    if ev is not None:
+                        torch.cuda.current_stream().wait_event(ev)
+                    if b > a:
+                        _lib.check(L.cymf_bpr_hogwild_range_dev(
+                            C.byref(f), self.dtype, self.opt, self.scatter, _lib.ptr(self.d_users[a:]),
+                            _lib.ptr(self.d_pos[a:]), b - a, _lib.ptr(self.d_indptr), _lib.ptr(self.d_indices),
+                            self.U, self.I, self.K, self.ld, learning_rate, weight_decay, self.seed,
+                            self.epochs_done, self.inflight, _lib.ptr(self.d_applied), a, stream))
+                self._ranges = []
         self.epochs_done += 1
 
     def download(self, W, H):

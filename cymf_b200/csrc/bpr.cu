@@ -22,7 +22,7 @@ template <typename T> struct BprArgs {
     const int32_t *users, *positives, *negatives;
     const int64_t *indptr;
     const int32_t *indices;
-    int64_t N, groups;
+    int64_t N, groups, first;     // `first`: position of users[0] in the epoch's pair list (Philox counter offset)
     int32_t I, ld;
     T lr, wd;
     uint64_t seed;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const BprArgs<T> a) {
         const int32_t u = u_next, i = i_next;
         const int64_t ln = l + stride;
         if (active && ln < a.N) { u_next = __ldcs(a.users + ln); i_next = __ldcs(a.positives + ln); }
-        const int32_t j = (int32_t)philox_negative(a.seed, a.epoch, (uint64_t)l, (uint32_t)a.I);   // bpr.pyx:165
+        const int32_t j = (int32_t)philox_negative(a.seed, a.epoch, (uint64_t)(l + a.first), (uint32_t)a.I);   // bpr.pyx:165
 
         // speculative gathers of the three rows (j is rarely a positive of u), issued before the membership probe
         T *pw = a.W + (size_t)u * a.ld, *pi = a.H + (size_t)i * a.ld, *pj = a.H + (size_t)j * a.ld;
@@ -288,6 +288,34 @@ static int dispatch_hogwild(const cymf_factors *f, int optimizer, int scatter, B
 
 using namespace cymf;
 
+extern "C" int cymf_bpr_hogwild_range_dev(const cymf_factors *f, int dtype, int optimizer, int scatter,
+                                          const int32_t *users, const int32_t *positives, int64_t N,
+                                          const int64_t *indptr, const int32_t *indices,
+                                          int32_t U, int32_t I, int32_t K, int32_t ld,
+                                          double learning_rate, double weight_decay,
+                                          uint64_t seed, uint32_t epoch, int64_t max_inflight,
+                                          unsigned long long *applied, int64_t first, void *stream) {
+    CYMF_REQUIRE(f && f->W && f->H && users && positives && indptr && indices, "null pointer");
+    CYMF_REQUIRE(U > 0 && I > 0 && K > 0 && ld >= K && ld % 4 == 0 && first >= 0, "bad shape (ld must be a multiple of 4, >= K)");
+    if (N <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CYMF_F32) {
+        BprArgs<float> a{};
+        a.users = users; a.positives = positives; a.indptr = indptr; a.indices = indices;
+        a.N = N; a.I = I; a.ld = ld; a.lr = (float)learning_rate; a.wd = (float)weight_decay;
+        a.seed = seed; a.epoch = epoch; a.applied = applied; a.first = first;
+        return dispatch_hogwild<float>(f, optimizer, scatter, a, max_inflight, st);
+    } else if (dtype == CYMF_F64) {
+        BprArgs<double> a{};
+        a.users = users; a.positives = positives; a.indptr = indptr; a.indices = indices;
+        a.N = N; a.I = I; a.ld = ld; a.lr = learning_rate; a.wd = weight_decay;
+        a.seed = seed; a.epoch = epoch; a.applied = applied; a.first = first;
+        return dispatch_hogwild<double>(f, optimizer, scatter, a, max_inflight, st);
+    }
+    set_error("bpr: unknown dtype %d", dtype);
+    return CYMF_EINVAL;
+}
+
 extern "C" int cymf_bpr_hogwild_epoch_dev(const cymf_factors *f, int dtype, int optimizer, int scatter,
                                           const int32_t *users, const int32_t *positives, int64_t N,
                                           const int64_t *indptr, const int32_t *indices,
@@ -295,25 +323,8 @@ extern "C" int cymf_bpr_hogwild_epoch_dev(const cymf_factors *f, int dtype, int 
                                           double learning_rate, double weight_decay,
                                           uint64_t seed, uint32_t epoch, int64_t max_inflight,
                                           unsigned long long *applied, void *stream) {
-    CYMF_REQUIRE(f && f->W && f->H && users && positives && indptr && indices, "null pointer");
-    CYMF_REQUIRE(U > 0 && I > 0 && K > 0 && ld >= K && ld % 4 == 0, "bad shape (ld must be a multiple of 4, >= K)");
-    if (N <= 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == CYMF_F32) {
-        BprArgs<float> a{};
-        a.users = users; a.positives = positives; a.indptr = indptr; a.indices = indices;
-        a.N = N; a.I = I; a.ld = ld; a.lr = (float)learning_rate; a.wd = (float)weight_decay;
-        a.seed = seed; a.epoch = epoch; a.applied = applied;
-        return dispatch_hogwild<float>(f, optimizer, scatter, a, max_inflight, st);
-    } else if (dtype == CYMF_F64) {
-        BprArgs<double> a{};
-        a.users = users; a.positives = positives; a.indptr = indptr; a.indices = indices;
-        a.N = N; a.I = I; a.ld = ld; a.lr = learning_rate; a.wd = weight_decay;
-        a.seed = seed; a.epoch = epoch; a.applied = applied;
-        return dispatch_hogwild<double>(f, optimizer, scatter, a, max_inflight, st);
-    }
-    set_error("bpr: unknown dtype %d", dtype);
-    return CYMF_EINVAL;
+    return cymf_bpr_hogwild_range_dev(f, dtype, optimizer, scatter, users, positives, N, indptr, indices, U, I, K, ld,
+                                      learning_rate, weight_decay, seed, epoch, max_inflight, applied, 0, stream);
 }
 
 extern "C" int cymf_bpr_replay_epoch_dev(const cymf_factors *f, int optimizer,

@@ -91,6 +91,17 @@ int cymf_bpr_hogwild_epoch_dev(const cymf_factors *f, int dtype, int optimizer, 
                                uint64_t seed, uint32_t epoch, int64_t max_inflight,
                                unsigned long long *applied, void *stream);
 
+/* The same pass over a RANGE of the epoch's pair list: users / positives point at pair `first`, N pairs follow; the
+ * negative of pair l is still keyed by (seed, epoch, first + l), so an epoch issued as several ranges -- e.g. while
+ * later ranges are still in flight over PCIe -- draws exactly the negatives of the single-launch epoch. */
+int cymf_bpr_hogwild_range_dev(const cymf_factors *f, int dtype, int optimizer, int scatter,
+                               const int32_t *users, const int32_t *positives, int64_t N,
+                               const int64_t *indptr, const int32_t *indices,
+                               int32_t U, int32_t I, int32_t K, int32_t ld,
+                               double learning_rate, double weight_decay,
+                               uint64_t seed, uint32_t epoch, int64_t max_inflight,
+                               unsigned long long *applied, int64_t first, void *stream);
+
 /* The negative the Hogwild kernels draw for triplets l = first .. first+count-1 of `epoch` (host-side
  * evaluation of the same Philox4x32-10 code), so that a run can be audited against the CPU oracle. */
 int cymf_bpr_negatives_host(uint64_t seed, uint32_t epoch, int64_t first, int64_t count, uint32_t n, int32_t *out);
