@@ -138,14 +138,14 @@ class BprSession(object):
             # Upload order = order of first use: factors and CSR first, then the pair list in ranges on a copy
             # stream, so that the first epoch starts on range 0 while the later ranges are still crossing PCIe
             # (the kernel needs every factor row from its first triplet on, but only the pairs it has reached).
+            self.d_users = torch.empty(N, dtype=torch.int32, device=dev)      # allocated first, filled last
+            self.d_pos = torch.empty(N, dtype=torch.int32, device=dev)
             self.d_indptr = torch.from_numpy(X.indptr.astype(np.int64)).to(dev, non_blocking=True)
             self.d_indices = torch.from_numpy(np.ascontiguousarray(X.indices, np.int32)).to(dev, non_blocking=True)
             self.dW = _lib.upload_factor(W, self.dtype, dev)
             self.dH = _lib.upload_factor(H, self.dtype, dev)
             src_u = torch.from_numpy(np.ascontiguousarray(users, np.int32))
             src_p = torch.from_numpy(np.ascontiguousarray(positives, np.int32))
-            self.d_users = torch.empty(N, dtype=torch.int32, device=dev)
-            self.d_pos = torch.empty(N, dtype=torch.int32, device=dev)
             self._ranges = []
             n_ranges = 4 if (N >= (1 << 22) and mode != "replay") else 1
             copy_stream = torch.cuda.Stream(device=dev) if n_ranges > 1 else torch.cuda.current_stream()

@@ -22,15 +22,19 @@ template <typename T> struct BprArgs {
     const int32_t *users, *positives, *negatives;
     const int64_t *indptr;
     const int32_t *indices;
-    int64_t N, groups, first;     // `first`: position of users[0] in the epoch's pair list (Philox counter offset)
+    int64_t N, groups;
     int32_t I, ld;
     T lr, wd;
     uint64_t seed;
     uint32_t epoch;
     unsigned long long *applied;
+    int64_t first, end;           // hogwild: the launch covers pairs [first, end) of the epoch; `users` / `positives` are
+                                  // pre-shifted by -first so that both they and the Philox counter are indexed by l
 };
 
-template <typename T, int OPT, int LPT, int NV, bool RED>
+// RANGE = false: the launch covers the whole epoch (first == 0) -- the code the throughput numbers are measured on.
+// RANGE = true : pairs [first, end) of the epoch (an epoch issued in pieces while later pieces cross PCIe).
+template <typename T, int OPT, int LPT, int NV, bool RED, bool RANGE>
 __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const BprArgs<T> a) {
     constexpr int GPW = 32 / LPT;
     const int lane = threadIdx.x & 31;
@@ -43,17 +47,19 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const BprArgs<T> a) {
 
     const int64_t gid = warp * GPW + lane / LPT;
     const bool active = gid < stride;
+#define CYMF_END (RANGE ? a.end : a.N)
     int64_t l = gid;
+    if constexpr (RANGE) l += a.first;
     int32_t u_next = 0, i_next = 0;
-    if (active && l < a.N) { u_next = __ldcs(a.users + l); i_next = __ldcs(a.positives + l); }
+    if (active && l < CYMF_END) { u_next = __ldcs(a.users + l); i_next = __ldcs(a.positives + l); }
 
     // warp-uniform trip count: the first group of the warp runs out last
     for (int64_t base = warp * GPW; base < a.N && warp * GPW < stride; base += stride, l += stride) {
-        const bool valid = active && l < a.N;
+        const bool valid = active && l < CYMF_END;
         const int32_t u = u_next, i = i_next;
         const int64_t ln = l + stride;
-        if (active && ln < a.N) { u_next = __ldcs(a.users + ln); i_next = __ldcs(a.positives + ln); }
-        const int32_t j = (int32_t)philox_negative(a.seed, a.epoch, (uint64_t)(l + a.first), (uint32_t)a.I);   // bpr.pyx:165
+        if (active && ln < CYMF_END) { u_next = __ldcs(a.users + ln); i_next = __ldcs(a.positives + ln); }
+        const int32_t j = (int32_t)philox_negative(a.seed, a.epoch, (uint64_t)l, (uint32_t)a.I);   // bpr.pyx:165
 
         // speculative gathers of the three rows (j is rarely a positive of u), issued before the membership probe
         T *pw = a.W + (size_t)u * a.ld, *pi = a.H + (size_t)i * a.ld, *pj = a.H + (size_t)j * a.ld;
@@ -138,6 +144,7 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const BprArgs<T> a) {
         for (int off = 16; off > 0; off >>= 1) n_applied += __shfl_xor_sync(0xffffffffu, n_applied, off);
         if (lane == 0 && n_applied) atomicAdd(a.applied, n_applied);
     }
+#undef CYMF_END
 }
 
 // ---- serialized f64 replay -------------------------------------------------------------------------------------
@@ -230,7 +237,7 @@ __global__ void __launch_bounds__(32) bpr_replay_kernel(const BprArgs<double> a,
 // ---- launch plumbing -----------------------------------------------------------------------------------------
 template <typename T, int OPT, int LPT, int NV, bool RED>
 static int launch_hogwild(const BprArgs<T> &a, int64_t max_groups, cudaStream_t st) {
-    auto kern = bpr_hogwild_kernel<T, OPT, LPT, NV, RED>;
+    auto kern = a.first > 0 ? bpr_hogwild_kernel<T, OPT, LPT, NV, RED, true> : bpr_hogwild_kernel<T, OPT, LPT, NV, RED, false>;
     int per_sm = 0;
     CYMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
     if (per_sm < 1) per_sm = 1;
@@ -243,6 +250,9 @@ static int launch_hogwild(const BprArgs<T> &a, int64_t max_groups, cudaStream_t 
     BprArgs<T> b = a;
     b.groups = blocks * GPB;
     if (max_groups > 0 && b.groups > max_groups) b.groups = max_groups;
+    b.end = a.first + a.N;
+    b.users = a.users - a.first;              // never dereferenced below index `first`
+    b.positives = a.positives - a.first;
     kern<<<(unsigned)blocks, 256, 0, st>>>(b);
     CYMF_LAUNCHED();
     return 0;
