@@ -383,6 +383,71 @@ def cpu_reference_bpr(train, users, positives, K, optimizer, budget_s=20.0, thre
             "sec_per_sample_epoch": per_epoch}
 
 
+def cpu_reference_extras():
+    """The compiled reference (oracle/_ref) timed on the host for the other paths, on bounded samples:
+    WMF on the full C2 shape, GloVe K=300 on 1 M samples, RelMF K=128 on a 500-user block.  Setup is removed by
+    differencing two fits where the API has no per-epoch hook."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    import cymf as ref
+    from cymf_b200 import synth
+    threads = os.cpu_count()
+    out = {}
+
+    def guarded(tag, fn):
+        try:
+            out[tag] = fn()
+        except Exception as ex:                              # noqa: BLE001 - a baseline must never cost the GPU line
+            out[tag] = {"failed": repr(ex)}
+
+    def wmf():
+        train, _, _ = dataset("ml-1m")
+        t = []
+        for e in (0, 3):
+            m = ref.WMF(64, 0.01, 10.0)
+            t0 = time.perf_counter()
+            m.fit(train, e, threads, verbose=False)
+            t.append(time.perf_counter() - t0)
+        return {"sec_per_epoch": max(t[1] - t[0], 1e-9) / 3, "cores": threads,
+                "sample": "cymf.WMF(64).fit on the full ml-1m shape (C2), (t(3 epochs) - t(0 epochs)) / 3"}
+
+    def glove():
+        V, n, K = 400_000, 1_000_000, 300
+        rng = np.random.default_rng(103)
+        c = rng.integers(0, V, n).astype(np.int32)
+        x = rng.integers(0, V, n).astype(np.int32)
+        cnt = np.maximum(np.exp(rng.normal(0.0, 1.5, n)), 0.1)
+        W, H = rng.uniform(-.5, .5, (V, K)) / K, rng.uniform(-.5, .5, (V, K)) / K
+        bw, bh = rng.uniform(-.5, .5, V) / K, rng.uniform(-.5, .5, V) / K
+        g = ref.GloVe(K, 0.05, 0.75, 10.0)
+        t = []
+        for e in (0, 2):
+            t0 = time.perf_counter()
+            g._fit_glove(c, x, cnt, W, bw, H, bh, e, 0.05, 10.0, 0.75, threads, False)
+            t.append(time.perf_counter() - t0)
+        return {"samples_per_s": 2 * n / max(t[1] - t[0], 1e-9), "cores": threads,
+                "sample": "cymf.GloVe(300)._fit_glove on 1 M uniform samples over a 400 k vocabulary, t(2 ep) - t(0 ep)"}
+
+    def relmf():
+        train, _, _ = dataset("ml-20m")
+        rows = 500
+        Xs = train[:rows]
+        t = []
+        for e in (0, 2):
+            m = ref.RelMF(128, 0.1, 0.01, "sgd", 0.01)
+            t0 = time.perf_counter()
+            m.fit(Xs, e, threads)
+            t.append(time.perf_counter() - t0)
+        n = rows * train.shape[1]
+        return {"samples_per_s": 2 * n / max(t[1] - t[0], 1e-9), "cores": threads,
+                "sample": f"cymf.RelMF(128, sgd).fit on the first {rows} users (dense {rows} x {train.shape[1]}), "
+                          f"{n} sampled cells per epoch, t(2 ep) - t(0 ep)"}
+
+    guarded("wmf_als_k64_ml1m", wmf)
+    guarded("glove_adagrad_k300", glove)
+    guarded("relmf_sgd_k128", relmf)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -506,6 +571,8 @@ def main():
         except Exception as ex:                                      # the checker is optional for the GPU number
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
 
+    if cpu is not None and not args.no_extra:
+        extra["cpu_reference"] = cpu_reference_extras()
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * secs_all / args.steps, "higher_is_better": True,
