@@ -12,6 +12,8 @@
 //                               Bound by the gather of H rows: sum_u n_u (8K + 4) + 8UK bytes.
 #include <math.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace cymf {
@@ -137,6 +139,16 @@ extern "C" int cymf_eval_candidates_host(int32_t U, int32_t I, const int32_t *te
     CYMF_REQUIRE(U > 0 && I > 0 && num_negatives >= 0, "bad shape");
     cymf_rng *gen = cymf_rng_create(seed);                                      // evaluator.pyx:82
     if (!gen) { set_error("out of memory"); return CYMF_ENOMEM; }
+    // Membership of a drawn item in the user's positives: one bit test in a per-call bitmap that holds the current
+    // user's positives (set before, cleared after the user's draws) instead of a binary search per draw -- the
+    // stream and the rejections are unchanged, only the lookup is cheaper (13.8 M draws at the ml-20m shape).
+    // Catalogues beyond 2^26 items keep the binary search.
+    std::vector<uint64_t> bits;
+    const bool use_bits = I <= (1 << 26);
+    if (use_bits) {
+        try { bits.assign(((size_t)I + 63) / 64, 0ull); }
+        catch (...) { cymf_rng_destroy(gen); set_error("out of memory"); return CYMF_ENOMEM; }
+    }
     int64_t w = 0;
     int32_t block[256];
     int filled = 0, used = 0;
@@ -148,15 +160,22 @@ extern "C" int cymf_eval_candidates_host(int32_t U, int32_t I, const int32_t *te
             if (w + (t1 - t0) + num_negatives > capacity) { set_error("cand_items too small"); rc = CYMF_EINVAL; break; }
             for (int32_t p = t0; p < t1; ++p) cand_items[w++] = test_indices[p];
             const int64_t a0 = all_indptr[u], a1 = all_indptr[u + 1];
+            if (use_bits)
+                for (int64_t p = a0; p < a1; ++p) bits[(size_t)all_indices[p] >> 6] |= 1ull << (all_indices[p] & 63);
             for (int32_t t = 0; t < num_negatives; ++t) {                       // evaluator.pyx:106-111
                 int32_t item;
+                bool positive;
                 do {
                     if (used == filled) { cymf_rng_fill_below(gen, (uint32_t)I, block, 256); filled = 256; used = 0; }
                     item = block[used++];
-                } while (a1 > a0 && all_indices[a0] <= item && item <= all_indices[a1 - 1] &&
-                         sorted_row_has(all_indices, a0, a1, item));
+                    if (use_bits) positive = (bits[(size_t)item >> 6] >> (item & 63)) & 1ull;
+                    else positive = a1 > a0 && all_indices[a0] <= item && item <= all_indices[a1 - 1] &&
+                                    sorted_row_has(all_indices, a0, a1, item);
+                } while (positive);
                 cand_items[w++] = item;
             }
+            if (use_bits)
+                for (int64_t p = a0; p < a1; ++p) bits[(size_t)all_indices[p] >> 6] = 0ull;
         }
         cand_ptr[u + 1] = w;
     }
