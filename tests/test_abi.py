@@ -133,3 +133,50 @@ def test_wmf_and_relmf_argument_validation():
     assert L.cymf_cooc_count_dev(None, None, 1 << 30, 10, 8, None, None, None, 0, None, None, None) == -1
     assert L.cymf_als_heavy_workspace_doubles(3, 128, 128) == 3 * (128 * 128 + 128)
     assert L.cymf_cooc_workspace_bytes(1000, 10) > 10000 * 20
+
+
+def _oracle_tokens(oracle, path, min_count):
+    x, i2w = oracle.read_text_vocabulary(path, min_count)
+    tokens = np.array([t for line in x for t in line], np.int32)
+    pos = np.array([p for line in x for p in range(len(line))], np.int32)
+    return tokens, pos, i2w
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_vocabulary_pass_equals_statement_for_statement_restatement(oracle, tmp_path, seed):
+    """cymf_b200.glove._vocabulary_pass (array operations) against the reference's loop restated statement for
+    statement (oracle.read_text_vocabulary, cymf/glove.pyx:198-214): random corpora with several lines, empty lines,
+    double spaces, rare words and words glued by newlines -- same ids, same positions, same KeyError."""
+    from cymf_b200.glove import _vocabulary_pass
+    rng = np.random.default_rng(seed)
+    vocab = [f"w{i}" for i in range(int(rng.integers(3, 40)))] + [""] * int(rng.integers(0, 3))
+    n_lines = int(rng.integers(1, 6))
+    lines = []
+    for _ in range(n_lines):
+        n = int(rng.integers(0, 60))
+        p = 1.0 / (np.arange(len(vocab)) + 1.0)
+        lines.append(" ".join(rng.choice(vocab, size=n, p=p / p.sum()).tolist()))
+    raw = "\n".join(lines) + ("\n" if rng.random() < 0.3 else "")
+    f = tmp_path / "c.txt"
+    f.write_text(raw)
+    min_count = int(rng.integers(1, 4))
+    try:
+        want = _oracle_tokens(oracle, str(f), min_count)
+    except KeyError as e:
+        with pytest.raises(KeyError) as got:
+            _vocabulary_pass(raw, min_count)
+        assert got.value.args == e.args
+        return
+    tokens, pos, i2w = _vocabulary_pass(raw, min_count)
+    assert np.array_equal(tokens, want[0]) and np.array_equal(pos, want[1])
+    assert i2w == want[2] and list(i2w) == list(want[2])                       # same map, same insertion order
+
+
+def test_vocabulary_pass_on_the_golden_corpora(oracle):
+    from conftest import GOLDEN
+    from cymf_b200.glove import _vocabulary_pass
+    for txt, mc in (("corpus_one_line.txt", 5), ("corpus_lines.txt", 3)):
+        path = os.path.join(GOLDEN, txt)
+        tokens, pos, i2w = _vocabulary_pass(open(path).read(), mc)
+        want = _oracle_tokens(oracle, path, mc)
+        assert np.array_equal(tokens, want[0]) and np.array_equal(pos, want[1]) and i2w == want[2]
