@@ -73,6 +73,7 @@ SIGNATURES = {
     "cymf_deal_rows_dev": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _p]),
     "cymf_csr_block_workspace_bytes": (_i64, [_i64]),
     "cymf_csr_block_dev": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _p, _p]),
+    "cymf_word2vec_write_host": (C.c_int, [C.c_char_p, _p, _i64, _i32, _p]),
     "cymf_cooc_workspace_bytes": (_i64, [_i64, _i32]),
     "cymf_cooc_count_dev": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _i64, _p, _p, _p]),
     "cymf_gram_workspace_doubles": (_i64, [_i64, _i32]),

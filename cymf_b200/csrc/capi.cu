@@ -4,6 +4,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <charconv>
+#include <cmath>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -385,5 +388,85 @@ extern "C" int cymf_relmf_fit_host(double *W, double *H, int32_t U, int32_t I, i
     CYMF_TRY(cymf_unpack_rows_dev(f.H, stage, dtype, I, K, ld, st));
     CYMF_CUDA(cudaMemcpyAsync(H, stage, (size_t)I * K * 8, cudaMemcpyDeviceToHost, st));
     CYMF_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- GloVe.save_word2vec_format (cymf/glove.pyx:164-177) ---------------------------------------------------------
+// The reference writes  f"{word} " + " ".join(map(str, W[i])) + "\n"  per row: str(np.float64) is the shortest
+// round-trip decimal laid out by CPython's repr rules.  std::to_chars (scientific) yields the same shortest digits;
+// the layout below restates format_float_short('r'): exponent form when decpt <= -4 or decpt > 16 (mantissa without
+// ".0", exponent of at least two digits), otherwise positional with ".0" appended to integral values.
+static char *py_float_repr(double x, char *out) {
+    if (x != x) { memcpy(out, "nan", 3); return out + 3; }
+    if (x < 0 || (x == 0 && std::signbit(x))) { *out++ = '-'; x = -x; }
+    if (x > 1.7976931348623157e308) { memcpy(out, "inf", 3); return out + 3; }
+    char buf[48];
+    const auto r = std::to_chars(buf, buf + sizeof(buf), x, std::chars_format::scientific);
+    char digits[24];
+    int nd = 0, exp10 = 0;
+    const char *p = buf;
+    for (; p < r.ptr && *p != 'e'; ++p)
+        if (*p != '.') digits[nd++] = *p;
+    if (p < r.ptr) {                                              // "e[+-]dd"
+        ++p;
+        const bool neg = *p == '-';
+        if (*p == '+' || *p == '-') ++p;
+        for (; p < r.ptr; ++p) exp10 = exp10 * 10 + (*p - '0');
+        if (neg) exp10 = -exp10;
+    }
+    while (nd > 1 && digits[nd - 1] == '0') --nd;                 // to_chars never pads, kept for safety
+    const int decpt = exp10 + 1;
+    if (decpt <= -4 || decpt > 16) {
+        *out++ = digits[0];
+        if (nd > 1) { *out++ = '.'; memcpy(out, digits + 1, nd - 1); out += nd - 1; }
+        *out++ = 'e';
+        int e = decpt - 1;
+        *out++ = e < 0 ? '-' : '+';
+        if (e < 0) e = -e;
+        char eb[8];
+        int ne = 0;
+        do { eb[ne++] = (char)('0' + e % 10); e /= 10; } while (e);
+        if (ne < 2) eb[ne++] = '0';
+        while (ne) *out++ = eb[--ne];
+    } else if (decpt <= 0) {
+        *out++ = '0'; *out++ = '.';
+        for (int z = 0; z < -decpt; ++z) *out++ = '0';
+        memcpy(out, digits, nd); out += nd;
+    } else if (decpt >= nd) {
+        memcpy(out, digits, nd); out += nd;
+        for (int z = 0; z < decpt - nd; ++z) *out++ = '0';
+        *out++ = '.'; *out++ = '0';
+    } else {
+        memcpy(out, digits, decpt); out += decpt;
+        *out++ = '.';
+        memcpy(out, digits + decpt, nd - decpt); out += nd - decpt;
+    }
+    return out;
+}
+
+// W: dense row-major f64 [V, K] HOST array; words: V NUL-terminated byte strings (already encoded).  Writes the
+// gensim word2vec text format byte for byte as the reference does.
+extern "C" int cymf_word2vec_write_host(const char *path, const double *W, int64_t V, int32_t K,
+                                        const char *const *words) {
+    CYMF_REQUIRE(path && (W || V == 0 || K == 0) && (words || V == 0) && V >= 0 && K >= 0, "bad argument");
+    FILE *f = fopen(path, "wb");
+    if (!f) { set_error("cannot open %s for writing", path); return CYMF_EINVAL; }
+    std::string line;
+    line = std::to_string(V) + " " + std::to_string(K) + "\n";
+    bool ok = fwrite(line.data(), 1, line.size(), f) == line.size();
+    std::vector<char> row((size_t)K * 32 + 16);
+    for (int64_t i = 0; i < V && ok; ++i) {
+        const size_t wl = strlen(words[i]);
+        ok = fwrite(words[i], 1, wl, f) == wl && fputc(' ', f) != EOF;
+        char *o = row.data();
+        for (int32_t k = 0; k < K; ++k) {
+            if (k) *o++ = ' ';
+            o = py_float_repr(W[(size_t)i * K + k], o);
+        }
+        *o++ = '\n';
+        ok = ok && fwrite(row.data(), 1, (size_t)(o - row.data()), f) == (size_t)(o - row.data());
+    }
+    if (fclose(f) != 0) ok = false;
+    if (!ok) { set_error("write to %s failed", path); return CYMF_EINVAL; }
     return 0;
 }

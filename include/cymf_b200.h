@@ -222,6 +222,12 @@ int cymf_csr_block_dev(const int64_t *indptr, const int32_t *indices, const int6
                        const int64_t *col_slot, int64_t *blk_indptr, int32_t *blk_indices, void *workspace,
                        void *stream);
 
+/* ---- GloVe.save_word2vec_format (cymf/glove.pyx:164-177) ------------------------------------------------------
+ * Writes "<V> <K>\n" and one line "<word> <w_0> ... <w_{K-1}>\n" per row, every value formatted exactly as the
+ * reference's str(np.float64) (shortest round-trip digits, CPython repr layout), so the file is byte-identical.
+ * W: dense f64 HOST [V, K]; words: V NUL-terminated, already encoded byte strings. */
+int cymf_word2vec_write_host(const char *path, const double *W, int64_t V, int32_t K, const char *const *words);
+
 /* ---- co-occurrence counting of read_text (cymf/glove.pyx:183-241, loop at :218-221) --------
  * For every kept token j of a line and every earlier kept token k of the same line with j - k <= window:
  * M[x_j, x_k] += 1.0 / (j - k).  tokens[n_tokens] = kept-word ids, lines concatenated; pos_in_line[n_tokens] = index

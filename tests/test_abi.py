@@ -180,3 +180,33 @@ def test_vocabulary_pass_on_the_golden_corpora(oracle):
         tokens, pos, i2w = _vocabulary_pass(open(path).read(), mc)
         want = _oracle_tokens(oracle, path, mc)
         assert np.array_equal(tokens, want[0]) and np.array_equal(pos, want[1]) and i2w == want[2]
+
+
+def test_save_word2vec_format_is_byte_identical(tmp_path):
+    """GloVe.save_word2vec_format through the C writer == the reference's Python loop (cymf/glove.pyx:164-177), byte for
+    byte: str(np.float64) is the shortest round-trip decimal in CPython's repr layout; random bit patterns over the
+    whole double range, layout thresholds (1e-4 / 1e-5, 1e15 / 1e16 / 1e17), zeros, subnormals, inf, nan."""
+    import cymf_b200 as cymf
+    rng = np.random.default_rng(0)
+    n = 60_000
+    bits = rng.integers(0, 2 ** 63, n, dtype=np.uint64) | (rng.integers(0, 2, n, dtype=np.uint64) << np.uint64(63))
+    special = np.array([0.0, -0.0, 1e-5, 9.999e-5, 1e-4, 0.001, 1e15, 1e16, 9999999999999998.0, 1e17, np.inf, -np.inf,
+                        np.nan, 5e-324, 1.7976931348623157e308, 2.2250738585072014e-308, 1.0, -1.0, 0.1, 123456.789,
+                        1e22, 1e23, 100.0, 12345678901234567890.0, 0.30000000000000004])
+    vals = np.concatenate([bits.view(np.float64), rng.normal(size=30_000), rng.normal(size=10_000) * 1e-5,
+                           10.0 ** rng.integers(-25, 25, 5_000).astype(float), special])
+    K = 25
+    W = vals[:(vals.shape[0] // K) * K].reshape(-1, K)
+    i2w = {i: f"wörd{i}" for i in range(W.shape[0])}
+    ref = tmp_path / "ref.vec"
+    with ref.open("w") as f:                                                   # the reference's loop, verbatim
+        f.write(f"{W.shape[0]} {W.shape[1]}\n")
+        for i in range(W.shape[0]):
+            f.write(f"{i2w[i]} " + " ".join(list(map(str, W[i]))) + "\n")
+    m = cymf.GloVe(K)
+    m.W = W
+    out = tmp_path / "new.vec"
+    m.save_word2vec_format(str(out), i2w)
+    assert out.read_bytes() == ref.read_bytes()
+    with pytest.raises(_lib.CymfError):
+        m.save_word2vec_format(str(tmp_path / "missing_dir" / "x.vec"), i2w)
