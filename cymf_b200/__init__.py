@@ -18,6 +18,7 @@ from .glove import GloVe
 from . import evaluator
 from .evaluator import Evaluator, AverageOverAllEvaluator, AoaEvaluator, UnbiasedEvaluator
 from . import synth
+from . import dataset
 
 __version__ = "0.1.0"
 

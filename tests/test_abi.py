@@ -210,3 +210,17 @@ def test_save_word2vec_format_is_byte_identical(tmp_path):
     assert out.read_bytes() == ref.read_bytes()
     with pytest.raises(_lib.CymfError):
         m.save_word2vec_format(str(tmp_path / "missing_dir" / "x.vec"), i2w)
+
+
+def test_synthetic_movielens_has_the_reference_dataset_shape():
+    import cymf_b200 as cymf
+    d = cymf.dataset.SyntheticMovieLens("ml-100k")
+    assert d.train.shape == d.valid.shape == d.test.shape == (943, 1682) == (d.num_user, d.num_item)
+    assert d.train.format == "lil" and (d.train_size, d.valid_size, d.test_size) == (d.train.nnz, d.valid.nnz, d.test.nnz)
+    total = d.train_size + d.valid_size + d.test_size
+    assert abs(d.test_size / total - 0.1) < 0.01 and abs(d.valid_size / total - 0.09) < 0.01
+    assert d.train.multiply(d.test).nnz == 0 and d.train.multiply(d.valid).nnz == 0      # disjoint splits
+    with pytest.raises(ValueError):
+        cymf.dataset.SyntheticMovieLens("ml-9000")
+    with pytest.raises(RuntimeError):
+        cymf.dataset.MovieLens("ml-100k")
