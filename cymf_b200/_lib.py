@@ -81,6 +81,7 @@ SIGNATURES = {
     "cymf_gram_finalize_dev": (C.c_int, [_p, C.c_int, _i32, _i32, _f64, _p, _p]),
     "cymf_als_cg_dev": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, C.c_int, _i32, _i32, _f64, _f64, _i32, _i32, _i32,
                                   _p, _p, _p]),
+    "cymf_als_rows_tc_dev": (C.c_int, [_p, _p, _p, _i32, _p, _p, C.c_int, _i32, _i32, _f64, _f64, _i32, _p, _p, _p]),
     "cymf_spd_inverse_dev": (C.c_int, [_p, _i32, _i32, _f64, C.c_int, _p, _p]),
     "cymf_chol_transforms_dev": (C.c_int, [_p, _i32, _i32, _f64, C.c_int, _p, _p, _p, _p, _p]),
     "cymf_rows_times_matrix_dev": (C.c_int, [_p, _p, _p, C.c_int, _i64, _i32, _p]),
@@ -179,11 +180,11 @@ class HostRng:
             self._h = None
 
 
-def upload_factor(host_f64, dtype, device):
+def upload_factor(host_f64, dtype, device, ld=None):
     """Dense f64 [rows, K] ndarray -> device [rows, ld] tensor of `dtype` with zeroed pad columns."""
     import torch
     rows, K = host_f64.shape
-    ld = ld_for(K)
+    ld = ld_for(K) if ld is None else int(ld)
     src = torch.from_numpy(host_f64).to(device, non_blocking=True)
     dst = torch.empty((rows, ld), dtype=torch.float32 if dtype == F32 else torch.float64, device=device)
     check(lib().cymf_pack_rows_dev(ptr(src), ptr(dst), dtype, rows, K, ld, stream_ptr()))

@@ -846,7 +846,7 @@ constexpr int MAX_DESTS = 8;
 template <typename T> struct MultiOut { T *p[MAX_DESTS]; int n; };
 
 template <typename T>
-__global__ void __launch_bounds__(256) rows_times_matrix_kernel(const T *__restrict__ in, const MultiOut<T> outs,
+__global__ void __launch_bounds__(256) rows_times_matrix_kernel(const T *in /* may alias a destination */, const MultiOut<T> outs,
                                                                 const T *__restrict__ B, int64_t rows, int ld) {
     extern __shared__ __align__(16) unsigned char smem_raw2[];
     T *Bs = reinterpret_cast<T *>(smem_raw2);          // [ld][ld]
@@ -1059,7 +1059,8 @@ extern "C" int cymf_als_half_host(const int32_t *indptr, const int32_t *indices,
     if (cg_tol <= 0) cg_tol = dtype == CYMF_F32 ? 1e-6 : 1e-10;
     if (cg_max_iter <= 0) cg_max_iter = 2 * K;
     const size_t es = dtype == CYMF_F32 ? 4 : 8;
-    const int32_t ld = (K + 3) / 4 * 4;
+    const bool tc_rows = dtype == CYMF_F32 && tc_enabled();            // one-pass tensor-core row solver (als_tc.cu)
+    const int32_t ld = tc_rows ? (K + 31) / 32 * 32 : (K + 3) / 4 * 4;
     const int64_t nnz = indptr[rows];
     std::vector<int64_t> ip64((size_t)rows + 1);
     std::vector<int32_t> order((size_t)rows);
@@ -1106,7 +1107,11 @@ extern "C" int cymf_als_half_host(const int32_t *indptr, const int32_t *indices,
     CYMF_TRY(cymf_chol_transforms_dev(g64, K, ld, 0.0, dtype, dBy, dBf, dBb, nullptr, st));
     CYMF_TRY(cymf_rows_times_matrix_dev(dY, dYt, dBy, dtype, n, ld, st));
     CYMF_TRY(cymf_rows_times_matrix_dev(dX, dX, dBf, dtype, rows, ld, st));
-    {   // heaviest rows with 16 warps per row, medium with 8, the rest with 4
+    if (tc_rows) {
+        CYMF_TRY(cymf_als_rows_tc_dev(d_ip, d_ix, d_order, (int32_t)rows, dX, dYt, dtype, K, ld, weight, cg_tol,
+                                      cg_max_iter, d_queue, d_stats, st));
+        CYMF_TRY(cymf_rows_times_matrix_dev(dX, dX, dBb, dtype, rows, ld, st));
+    } else {   // heaviest rows with 16 warps per row, medium with 8, the rest with 4
         std::vector<int64_t> len((size_t)rows);
         for (int64_t t = 0; t < rows; ++t) len[(size_t)t] = indptr[order[(size_t)t] + 1] - indptr[order[(size_t)t]];
         int64_t n16 = 0, n8 = 0;

@@ -42,6 +42,9 @@ int tc_gram_partial(const float *Y, int64_t n, int K, int ld, double *partial, c
 int tc_gram_gather(const float *Y, const int64_t *indptr, const int32_t *indices, const int32_t *order,
                    const int32_t *first_slab, int n_heavy, int n_slabs, int K, int ld, double *partial, double *bsum,
                    cudaStream_t st);
+int tc_als_rows(const int64_t *indptr, const int32_t *indices, const int32_t *order, int32_t n_solve, float *X,
+                const float *Y, int ld, float weight, float tol2, int32_t max_iter, int32_t *queue,
+                unsigned long long *stats, cudaStream_t st);      // als_tc.cu
 bool tc_enabled();      // false when the environment sets CYMF_NO_TCGEN05=1 (A/B comparisons in tests and tools)
 
 #define CYMF_TRY(expr)             \

@@ -66,17 +66,26 @@ class Evaluator(object):
 
     def _device_candidates(self, seed, dev):
         import torch
-        key = (int(seed), str(dev))
+        # the lists depend on the seed, on num_negatives and on the two CSR structures: all of them are public
+        # attributes, so all of them are part of the cache key (changing one after a first evaluate() rebuilds)
+        key = (int(seed), str(dev), int(self.num_negatives), id(self.X), int(self.X.nnz), id(self.user_positives),
+               int(self.user_positives.nnz))
         if key not in self._cand:
             cand_ptr, cand_items = self.candidates(seed)
             self._cand = {key: (torch.from_numpy(cand_ptr).to(dev), torch.from_numpy(cand_items).to(dev),
                                 int(np.diff(cand_ptr).max()) if cand_ptr.shape[0] > 1 else 0)}
-        if self._dev_csr is None or self._dev_csr[0] != str(dev):
-            self._dev_csr = (str(dev), torch.from_numpy(np.ascontiguousarray(self.X.indptr, np.int32)).to(dev))
+        csr_key = (str(dev), id(self.X), int(self.X.nnz))
+        if self._dev_csr is None or self._dev_csr[0] != csr_key:
+            self._dev_csr = (csr_key, torch.from_numpy(np.ascontiguousarray(self.X.indptr, np.int32)).to(dev))
         return self._cand[key], self._dev_csr[1]
 
     # ---- evaluate ------------------------------------------------------------------------------------------------
     def evaluate(self, W, H, seed=1234, return_order=False):
+        """`Evaluator.evaluate(W, H, seed)` (evaluator.pyx:57-139).  Ranking is exact and deterministic: candidates are
+        ordered by decreasing f64 score, and EQUAL scores rank by decreasing candidate position (the order the
+        reference's `argsort()[::-1]` gives for runs of equal keys under a stable sort; NumPy's default quicksort is
+        not stable, so on exact ties -- e.g. a user whose W row is all zero, as WMF leaves users without training
+        entries -- the reference's own order is unspecified and may differ)."""
         if self.unbiased:
             raise NotImplementedError("UnbiasedEvaluator (IPS metrics, evaluator.pyx:115-123) is out of scope of "
                                       "cymf_b200; use AverageOverAllEvaluator")

@@ -179,7 +179,14 @@ class AlsSession(object):
         self.dtype = _lib.DTYPES[dtype]
         self.tdt = tdt = torch.float32 if self.dtype == _lib.F32 else torch.float64
         self.K = K = int(K if K is not None else W.shape[1])
-        self.ld = ld = _lib.ld_for(K)
+        # Row solver of the half sweep.  "tc": one pass over the row -- S = sum y~ y~^T on the tensor cores, CG out of
+        # registers (cymf_als_rows_tc_dev; f32, K <= 128, transformed coordinates; rows are padded to a multiple of
+        # 32 columns).  "cg": the streaming CG kernel (f64, or CYMF_ALS_ROWS=cg / CYMF_NO_TCGEN05=1 for A/B runs).
+        self.row_solver = "cg"
+        if (self.dtype == _lib.F32 and K <= 128 and solver == "transformed" and os.environ.get("CYMF_NO_TCGEN05") != "1"
+                and os.environ.get("CYMF_ALS_ROWS", "tc") == "tc"):
+            self.row_solver = "tc"
+        self.ld = ld = (K + 31) // 32 * 32 if self.row_solver == "tc" else _lib.ld_for(K)
         self.wd, self.weight = float(weight_decay), float(weight)
         self.cg_tol, self.cg_max_iter, self.stage_rows = float(cg_tol), int(cg_max_iter), int(stage_rows)
         self.prep = prep
@@ -216,6 +223,7 @@ class AlsSession(object):
             self.Yt = torch.empty((max(Up, Ip), ld), dtype=tdt, device=dev)     # fixed side in transformed coordinates
             self.queue = torch.zeros(4, dtype=torch.int32, device=dev)     # one work-queue head per row class
             self.d_stats = torch.zeros(2, dtype=torch.int64, device=dev)
+            self.d_info = torch.zeros(1, dtype=torch.int32, device=dev)    # Cholesky pivot failures (checked in stats())
         self.epochs_done = 0
         self.h2d_bytes = self._nbytes(W) + self._nbytes(H) + 8 * (self.Ru + self.Ri + 2) + 4 * sum(self.block_nnz)
         self.d2h_bytes = self._nbytes(W) + self._nbytes(H)
@@ -295,7 +303,10 @@ class AlsSession(object):
                 moved.append((name, new, hdl, ptrs))
             ok = torch.ones(1, device=self.dev)
         except Exception as exc:                                   # noqa: BLE001 - any failure -> NCCL path
+            import warnings
             self.peer_error = repr(exc)
+            warnings.warn(f"cymf_b200.WMF: symmetric (NVLink peer) memory unavailable, blocks are exchanged with NCCL "
+                          f"all-gather instead: {self.peer_error}", RuntimeWarning)
             ok = torch.zeros(1, device=self.dev)
             moved = []
         self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)        # all ranks take the same path
@@ -313,8 +324,10 @@ class AlsSession(object):
         if isinstance(host, np.ndarray) and self.prep != "device":
             dealt = np.zeros((slots.shape[0], host.shape[1]), np.float64)
             dealt[slots >= 0] = host[slots[slots >= 0]]
-            return _lib.upload_factor(dealt, self.dtype, self.dev)
-        t = _lib.upload_factor(host, self.dtype, self.dev) if isinstance(host, np.ndarray) else host
+            return _lib.upload_factor(dealt, self.dtype, self.dev, self.ld)
+        t = _lib.upload_factor(host, self.dtype, self.dev, self.ld) if isinstance(host, np.ndarray) else host
+        if t.shape[1] < self.ld:                                   # device tensor narrower than the session's row stride
+            t = torch.cat([t, torch.zeros((t.shape[0], self.ld - t.shape[1]), dtype=t.dtype, device=t.device)], 1)
         d_slots = self.d_slot_u if slots is self.slot_u else self.d_slot_i
         t = torch.cat([t, torch.zeros((1, t.shape[1]), dtype=t.dtype, device=t.device)])     # row for the phantoms
         return t.index_select(0, torch.where(d_slots >= 0, d_slots, t.shape[0] - 1))
@@ -376,7 +389,7 @@ class AlsSession(object):
             # G = L L^T; in the coordinates y~ = L^-1 y, x~ = L^T x the row systems are (I + (w-1) sum y~ y~^T) x~ =
             # w sum y~, so the CG iteration carries no dense K x K product (three skinny GEMMs per half sweep instead)
             _lib.check(L.cymf_chol_transforms_dev(_lib.ptr(self.g64), K, ld, add_diag, self.dtype, _lib.ptr(self.By),
-                                                  _lib.ptr(self.Bfwd), _lib.ptr(self.Bbwd), None, stream))
+                                                  _lib.ptr(self.Bfwd), _lib.ptr(self.Bbwd), _lib.ptr(self.d_info), stream))
             yt = self.Yt[:Y_full.shape[0]]
             _lib.check(L.cymf_rows_times_matrix_dev(_lib.ptr(Y_full), _lib.ptr(yt), _lib.ptr(self.By), self.dtype,
                                                     Y_full.shape[0], ld, stream))
@@ -411,6 +424,14 @@ class AlsSession(object):
                     done.record(st)
                     joins.append(done)
             start = nh
+        if self.row_solver == "tc":
+            count = sum(classes)
+            if count:
+                _lib.check(L.cymf_als_rows_tc_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order[start:]), count,
+                                                  _lib.ptr(x_blk), _lib.ptr(y_used), self.dtype, K, ld, self.weight,
+                                                  self.cg_tol, self.cg_max_iter, _lib.ptr(self.queue),
+                                                  _lib.ptr(self.d_stats), _lib.stream_ptr()))
+            classes = (0, 0, 0)
         for c, (width, count) in enumerate(zip((16, 8, 4), classes)):
             if count:
                 st = self._side[c] if (c < 2 and self.overlap_classes) else main
@@ -489,6 +510,13 @@ class AlsSession(object):
         self.dH.copy_(snap[1])
 
     def stats(self):
+        """(CG iterations summed over rows, rows that stopped at cg_max_iter).  Raises if a Gram matrix Y^T Y + wd I
+        was not numerically positive definite (weight_decay = 0 with rank-deficient factors): the reference's dgesv
+        has no such requirement, the Cholesky change of variables does."""
+        info = int(self.d_info.item())
+        if info:
+            raise _lib.CymfError(f"WMF: Y^T Y + weight_decay I is not positive definite (pivot {info}); use "
+                                 "weight_decay > 0 or solver='cg'")
         s = self.d_stats.cpu().numpy()
         return int(s[0]), int(s[1])
 

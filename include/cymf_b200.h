@@ -306,6 +306,16 @@ int cymf_als_heavy_rows_dev(const int64_t *indptr, const int32_t *indices, const
                             double add_diag, int dtype, int32_t K, int32_t ld, double weight, double *workspace,
                             int64_t workspace_doubles, void *stream);
 
+/* One-pass row solver (f32, ld in {32,64,96,128}, factors in the transformed coordinates of
+ * cymf_chol_transforms_dev): per row the K x K matrix S = sum_{i in row} y~_i y~_i^T that the reference accumulates
+ * entry by entry (cymf/wmf.pyx:161-166) is built ONCE on the tensor cores (tcgen05 3xTF32, TMEM accumulators) from a
+ * single gather of the row's item vectors, then (I + (weight-1) S) x~ = weight sum y~_i (wmf.pyx:163,168) is solved
+ * by conjugate gradient out of registers (same stopping rule and statistics as cymf_als_cg_dev).  Rows without
+ * entries are zeroed (wmf.pyx:154-156).  Other dtypes / strides: CYMF_EUNSUPPORTED (use cymf_als_cg_dev). */
+int cymf_als_rows_tc_dev(const int64_t *indptr, const int32_t *indices, const int32_t *order, int32_t n_solve,
+                         void *X, const void *Y, int dtype, int32_t K, int32_t ld, double weight, double cg_tol,
+                         int32_t cg_max_iter, int32_t *queue, unsigned long long *stats, void *stream);
+
 /* warps_per_row of cymf_als_cg_dev is 4, 8 or 16 (CTA width per row; each warp brings 8 KB of shared-memory
  * staging for the row's item vectors).  Given the row lengths in `order` (decreasing), this returns how many
  * leading rows should be solved with 16 warps and how many following ones with 8; the rest take 4. */

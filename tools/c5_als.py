@@ -66,6 +66,7 @@ def main():
     ap.add_argument("--heavy-min", type=int, default=4096, help="rows with at least this many entries are solved directly")
     ap.add_argument("--no-overlap", action="store_true", help="row-class kernels back to back on one stream")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--cg-tol", type=float, default=1e-6, help="1e10 = no CG iterations (times the per-row Gram build alone)")
     args = ap.parse_args()
 
     import torch.distributed as dist
@@ -93,14 +94,14 @@ def main():
 
     g = torch.Generator(device=dev)
     g.manual_seed(4321)
-    ld = _lib.ld_for(K)
+    ld = (K + 31) // 32 * 32
     W = (torch.rand((U, ld), device=dev, generator=g) * 0.2 - 0.1) / K         # wmf.pyx:88-92 on the device, f32
     H = (torch.rand((I, ld), device=dev, generator=g) * 0.2 - 0.1) / K
     W[:, K:] = 0
     H[:, K:] = 0
     launches0 = _lib.launch_count()
     t0 = time.perf_counter()
-    sess = AlsSession((indptr, indices, (U, I)), W, H, 0.01, 10.0, K=K, dtype="float32", cg_tol=1e-6, cg_max_iter=2 * K,
+    sess = AlsSession((indptr, indices, (U, I)), W, H, 0.01, 10.0, K=K, dtype="float32", cg_tol=args.cg_tol, cg_max_iter=2 * K,
                       stage_rows=args.stage_rows, overlap_classes=not args.no_overlap, heavy_min=args.heavy_min)
     sync()
     t_prep = time.perf_counter() - t0
@@ -161,7 +162,7 @@ def main():
         if args.out:
             with open(args.out, "w") as f:
                 f.write(json.dumps(line) + "\n")
-        assert finite and float(res.max()) <= 1e-4, line
+        assert finite and (float(res.max()) <= 1e-4 or args.cg_tol > 1e-6), line
     if world > 1:
         dist.destroy_process_group()
 
