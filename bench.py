@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- the driver's benchmark contract for cymf_b200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-extra] [--no-cpu]
 
-Metric (BASELINE.json): BPR triplet-updates/sec.  A "step" is one epoch of the BPR hot loop
-(cymf/bpr.pyx:162-169) over the shuffled (user, positive) pairs of a synthetic ml-20m-shaped matrix
-(138,493 x 26,744, 20 M nnz before the 10 % hold-out; BASELINE.json configs[2], K=128, SGD, f32 storage).
-`value`   = applied (non-colliding) updates of all ranks / max-over-ranks device time, factors, pairs and
-            CSR resident in HBM.  At N>1 BPR does not shard (every triplet may touch any
-            row), so each rank trains an independent replica: "replicas only", scaling "weak".
-`e2e`     = same metric through the reference-facing typed boundary `BPR._fit_bpr(users, positives, X, 1,
-            lr, wd, ...)` with HOST numpy buffers: H2D of pairs, CSR and both f64 factors and D2H of the
-            factors are inside the timed region every step.
-`roofline`= algorithmic bytes of the epoch kernel (6*K*4+8 B per applied update) / its CUDA-event duration,
-            against MEASURED_PEAKS.json's HBM copy bandwidth.
-`cpu_baseline` = the compiled reference (oracle/_ref, OpenMP, all host cores) on a row-block sample.
-`extra`   = the other hot-path kernels on their BASELINE.json configs (K=64 target run, Adam, ALS, GloVe, ...).
+Metric (BASELINE.json: "WMF ALS sec/epoch at 1/2/4/8 B200", reported as its reciprocal so that higher is better and
+the driver's strong-scaling efficiency is value_N / (N value_1)): `wmf_als_epochs_per_sec`.  A "step" is one epoch
+of `WMF._fit_als` (cymf/wmf.pyx:110-112: user half sweep + item half sweep of `_als`, wmf.pyx:136-174) at K=128 on
+the synthetic ml-20m-shaped matrix (138,493 x 26,744, 20 M nnz before the 10 % hold-out) -- the configuration the
+north star's "< 50 ms on 8 B200" target is quoted on.  At N>1 the SAME matrix is sharded by user / item row blocks
+over the ranks: "scaling": "strong".
+`value`   = epochs / max-over-ranks device time, CSR blocks and factors resident in HBM.
+`e2e`     = the same metric through the public call `WMF.fit(X, 1)` with HOST (pinned) numpy buffers: upload of the
+            CSR and both f64 factor matrices, device-side preparation, one epoch, download of both factors, every step.
+`roofline`= algorithmic bytes of the row-solver launches (N (K s + 4) + rows (K s + 8) per half sweep, SURVEY.md
+            8(d)) / their CUDA-event durations, against MEASURED_PEAKS.json's HBM copy bandwidth.
+`parity`  = float64 relative residual of the reference's per-row normal equations (wmf.pyx:161-168) on sampled rows
+            + the heaviest row of every rank's block, after one more user and item half sweep; max over ranks.
+`cpu_baseline` = the compiled reference (oracle/_ref, OpenMP, all host cores) `WMF._als` on every 20th user row and
+            every 20th item row, extrapolated by the row ratio (labelled).
+`extra`   = the other hot-path kernels on their BASELINE.json configs: BPR (the other half of BASELINE.json's metric:
+            K=128 / K=64 / Adam / f64 with their own roofline blocks and e2e), C1 epochs/s, WMF C2 and C5, GloVe
+            C4, RelMF, evaluator.
 """
 import argparse
 import json
@@ -30,10 +35,28 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-METRIC = "bpr_triplet_updates_per_sec"
-UNIT = "updates/s"
-WORKLOAD = "bpr-sgd-f32 K=128 on synthetic ml-20m-shaped CSR (138493x26744, 20M nnz, 10% held out)"
+METRIC = "wmf_als_epochs_per_sec"
+UNIT = "epochs/s"
+WORKLOAD = ("wmf-als-f32 K=128 weight_decay=0.01 weight=10 on synthetic ml-20m-shaped CSR (138493x26744, 20M nnz, "
+            "10% held out); one step = one epoch (user + item half sweep); rows sharded over the ranks")
+ALS_WD, ALS_WEIGHT = 0.01, 10.0
+CPU_STRIDE = 20            # the CPU arms solve every 20th user row and every 20th item row of the same matrix
+CPU_SAMPLE = (f"compiled reference cymf.WMF(128, 0.01, 10.0)._als (cymf/wmf.pyx:136) on every {CPU_STRIDE}th user row and "
+              f"every {CPU_STRIDE}th item row of the workload with the full fixed side, all host threads; epoch time = "
+              f"t_user_rows x {CPU_STRIDE} + t_item_rows x {CPU_STRIDE} (row-ratio extrapolation)")
+BPR_UNIT = "updates/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per row-solver launch from the committed ncu --set full capture
+# (profiles/, same kernel, C5-scale matrix whose fixed side does not fit L2); None until captured for this round
+ROOFLINE_TRAFFIC = None
 LR, WD, K_MAIN = 0.01, 0.01, 128
+
+
+def config_block(world):
+    """Identical in both arms (the reference arm computes in f64 on the host and is sampled; both facts are stated)."""
+    return {"workload": WORKLOAD, "K": K_MAIN, "weight_decay": ALS_WD, "weight": ALS_WEIGHT,
+            "cpu_arm_sample": CPU_SAMPLE,
+            "l2": "no explicit flush: one epoch streams 18.7 GB of gathered rows (user side 71 MB + item side 14 MB of "
+                  "factors fit the 126 MB L2, which is part of the workload's nature at this shape)"}
 CACHE = os.environ.get("CYMF_BENCH_CACHE", "/tmp/cymf_b200_cache")
 
 
@@ -202,50 +225,64 @@ def time_evaluator(name, K, steps, hbm, with_reference):
     return out
 
 
-def time_als_device_pipeline(scale, K, steps, hbm):
-    """BASELINE configs[4] pipeline at `scale` of 10 M x 1 M x 1 B nnz on ONE GPU: matrix generated on the device,
-    X^T / row deal / blocks by prep.cu, device-initialised factors (tools/c5_als.py runs the full size, 1-8 GPUs)."""
+def time_als_device_pipeline(scale, K, steps, hbm, world=1, sync_all=None):
+    """BASELINE configs[4] pipeline at `scale` of 10 M x 1 M x 1 B nnz: matrix generated on every rank's GPU (same
+    seed, identical), X^T / row deal / this rank's blocks by prep.cu, device-initialised factors, row blocks sharded
+    over the ranks; normal-equation residual of one more epoch as the parity scalar."""
     import torch
-    from cymf_b200 import _lib
+    import torch.distributed as dist
     from cymf_b200.synth import synth_implicit_device
     from cymf_b200.wmf import AlsSession
+    sync_all = sync_all or torch.cuda.synchronize
     U, I, nnz = int(10_000_000 * scale), int(1_000_000 * scale), int(1_000_000_000 * scale)
     ip, ix = synth_implicit_device(U, I, nnz, seed=104)
     real_nnz = int(ix.numel())
     g = torch.Generator(device="cuda")
     g.manual_seed(4321)
-    ld = _lib.ld_for(K)
+    ld = (K + 31) // 32 * 32
     W = (torch.rand((U, ld), device="cuda", generator=g) * 0.2 - 0.1) / K
     H = (torch.rand((I, ld), device="cuda", generator=g) * 0.2 - 0.1) / K
     W[:, K:] = 0
     H[:, K:] = 0
-    torch.cuda.synchronize()
+    sync_all()
     t0 = time.perf_counter()
-    s = AlsSession((ip, ix, (U, I)), W, H, 0.01, 10.0, K=K, distributed=False)
-    torch.cuda.synchronize()
+    s = AlsSession((ip, ix, (U, I)), W, H, 0.01, 10.0, K=K, distributed=world > 1)
+    sync_all()
     prep_s = time.perf_counter() - t0
     del W, H, ip, ix
+    torch.cuda.empty_cache()
     for _ in range(2):
         s.epoch()
-    torch.cuda.synchronize()
+    sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         s.epoch()
     e1.record()
-    torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) * 1e-3 / steps
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3 / steps], dtype=torch.float64, device="cuda")
+    s.user_half()
+    ru = s.residual("user", 12, seed=11 + s.rank)
+    s.item_half()
+    ri = s.residual("item", 12, seed=12 + s.rank)
+    r = torch.tensor([ru, ri], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r, op=dist.ReduceOp.MAX)
+    sec = float(t[0])
     algo = 2 * real_nnz * (K * 4 + 4) + (U + I) * (K * 4 + 8) + (U + I) * K * 4
-    out = {"sec_per_epoch": sec, "shape": [U, I], "nnz": real_nnz, "K": K, "prepare_on_device_sec": prep_s,
-           "algorithmic_GBps": algo / sec / 1e9, "frac_of_hbm_peak": algo / sec / 1e9 / hbm,
-           "unconverged_rows": s.stats()[1],
-           "full_size": "tools/c5_als.py: 0.90 s/epoch on 1 B200, 0.168 s on 8 (profiles/r1_c5_als_*.json)"}
+    out = {"sec_per_epoch": sec, "n_gpus": world, "shape": [U, I], "nnz": real_nnz, "K": K,
+           "prepare_on_device_sec": prep_s, "algorithmic_GBps_all_gpus": algo / sec / 1e9,
+           "frac_of_hbm_peak_per_gpu": algo / sec / 1e9 / (hbm * world), "unconverged_rows": s.stats()[1],
+           "row_solver": s.row_solver, "gather": "peer-store" if s.peer else ("nccl" if s.dist else "single"),
+           "parity_rel_residual": {"user_rows": float(r[0]), "item_rows": float(r[1]), "rows_checked_per_side_per_rank": 13},
+           "hbm_peak_allocated_GB": torch.cuda.max_memory_allocated() / 1e9}
     del s
     torch.cuda.empty_cache()
     return out
 
 
-def time_bpr_e2e(train, users, positives, K, optimizer, steps, warmup, lr=LR, wd=WD):
+def time_bpr_e2e(train, users, positives, K, optimizer, steps, warmup, lr=LR, wd=WD, dtype="float32"):
     """Through the typed boundary with host buffers: every step uploads inputs and downloads the factors."""
     import torch
     import cymf_b200 as cymf
@@ -258,7 +295,7 @@ def time_bpr_e2e(train, users, positives, K, optimizer, steps, warmup, lr=LR, wd
     users, positives = pinned(users), pinned(positives)
     train = sparse.csr_matrix((train.data, pinned(train.indices), pinned(train.indptr)), shape=train.shape, copy=False)
     train.has_sorted_indices = True
-    m = cymf.BPR(K, lr, optimizer, wd)
+    m = cymf.BPR(K, lr, optimizer, wd, dtype=dtype)
     m.W, m.H = (pinned(a) for a in init_factors(train.shape[0], train.shape[1], K))
     m.valid_evaluator, m.early_stopping = None, False
     applied, h2d, d2h = 0, 0, 0
@@ -285,7 +322,7 @@ def time_als(train, K, dtype, steps, warmup, sync_all, world, hbm):
     from cymf_b200.host import init_factors
     W, H = init_factors(train.shape[0], train.shape[1], K)
     s = AlsSession(train, W, H, 0.01, 10.0, dtype=dtype, cg_tol=1e-6 if dtype == "float32" else 1e-10,
-                   cg_max_iter=2 * K)
+                   cg_max_iter=2 * K, distributed=world > 1)
     for _ in range(warmup):
         s.epoch()
     sync_all()
@@ -305,7 +342,12 @@ def time_als(train, K, dtype, steps, warmup, sync_all, world, hbm):
            "gather": "peer-store (fused into the GEMM epilogue)" if s.peer else ("nccl all-gather" if s.dist else "single"),
            "cg_iterations_per_row": (s.stats()[0] - it0) / (steps * 2 * rows) * 2, "cg_tol": s.cg_tol,
            "unconverged_rows": s.stats()[1], "algorithmic_GBps": s.bytes_per_epoch / sec / 1e9,
-           "frac_of_hbm_peak": s.bytes_per_epoch / sec / 1e9 / (hbm * world)}
+           "frac_of_hbm_peak": s.bytes_per_epoch / sec / 1e9 / (hbm * world), "row_solver": s.row_solver}
+    s.user_half()
+    r = torch.tensor([s.residual("user", 12, seed=7 + s.rank)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(r, op=dist.ReduceOp.MAX)
+    out["parity_rel_residual_user_rows"] = float(r[0])
     del s
     torch.cuda.empty_cache()
     return out
@@ -375,8 +417,9 @@ def cpu_reference_bpr(train, users, positives, K, optimizer, budget_s=20.0, thre
     t1 = fit(e1)
     t2 = fit(e2)
     per_epoch = max((t2 - t1) / (e2 - e1), 1e-9)
-    accept = 1.0 - float(np.mean(np.diff(Xs.indptr))) / train.shape[1]   # E[1 - deg_u / I] over pairs ~ this
-    return {"value": n * accept / per_epoch, "unit": UNIT, "cores": threads, "kind": "reference",
+    deg = np.diff(Xs.indptr).astype(np.float64)
+    accept = 1.0 - float((deg * deg).sum()) / (max(n, 1) * train.shape[1])   # E over PAIRS of 1 - deg_u / I
+    return {"value": n * accept / per_epoch, "unit": BPR_UNIT, "cores": threads, "kind": "reference",
             "sample": f"first {rows} users of the workload ({n} pairs/epoch), cymf.BPR(K={K},{optimizer}).fit "
                       f"num_threads={threads}, (t({e2} ep)-t({e1} ep))/{e2 - e1}; attempts x expected acceptance "
                       f"{accept:.4f}",
@@ -449,20 +492,178 @@ def cpu_reference_extras():
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_als(train, K, steps, warmup, threads=None):
+    """The compiled reference's `WMF._als` (oracle/_ref, cymf/wmf.pyx:136-174) on a strided row sample of BOTH half
+    sweeps of the workload; every step solves the same sample.  Returns the cpu_baseline block (value in epochs/s,
+    extrapolated by the row ratio) and the per-step sample seconds."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    import cymf as ref                                                  # the reference build, not cymf_b200
+    from cymf_b200.host import init_factors
+    threads = threads or os.cpu_count()
+    U, I = train.shape
+    W, H = init_factors(U, I, K)
+    XT = train.T.tocsr()
+    ru, ri = np.arange(0, U, CPU_STRIDE), np.arange(0, I, CPU_STRIDE)
+    Xu, Xi = train[ru].tocsr(), XT[ri].tocsr()
+    Wb, Hb = np.ascontiguousarray(W[ru]), np.ascontiguousarray(H[ri])
+    m = ref.WMF(K, ALS_WD, ALS_WEIGHT)
+    ipu, ixu = Xu.indptr.astype(np.int32), Xu.indices.astype(np.int32)
+    ipi, ixi = Xi.indptr.astype(np.int32), Xi.indices.astype(np.int32)
+    per = []
+    for t in range(warmup + steps):
+        t0 = time.perf_counter()
+        m._als(ipu, ixu, Wb, H, threads)
+        t1 = time.perf_counter()
+        m._als(ipi, ixi, Hb, W, threads)
+        t2 = time.perf_counter()
+        if t >= warmup:
+            per.append(((t1 - t0) * U / ru.shape[0] + (t2 - t1) * I / ri.shape[0], t2 - t0))
+    epoch = float(np.mean([p[0] for p in per]))
+    return {"value": 1.0 / epoch, "unit": UNIT, "cores": threads, "kind": "reference", "sample": CPU_SAMPLE,
+            "sec_per_epoch_extrapolated": epoch, "sec_per_sample_step": float(np.mean([p[1] for p in per])),
+            "sample_rows": [int(ru.shape[0]), int(ri.shape[0])], "sample_nnz": [int(Xu.nnz), int(Xi.nnz)],
+            "dtype": "f64"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    train, users, positives = dataset("ml-20m")
-    # each "step" = one epoch over the bounded sample; W warm-up epochs and K timed ones by differencing
-    base = cpu_reference_bpr(train, users, positives, K_MAIN, "sgd", epochs=(args.warmup, args.warmup + args.steps))
+    train, _, _ = dataset("ml-20m")
+    base = cpu_reference_als(train, K_MAIN, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["sec_per_sample_epoch"] * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference computes in f64 on the host"},
-            "cpu_baseline": base,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["sec_per_sample_step"] * 1e3,
+            "sec_per_epoch": base["sec_per_epoch_extrapolated"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_block(args.gpus), "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def time_als_main(train, K, steps, warmup, sync_all, world, hbm):
+    """The headline: device-resident epochs of the sharded ALS session, per-epoch CUDA events, the row-solver
+    launches timed with their own events, and the normal-equation residual of one more epoch."""
+    import torch
+    import torch.distributed as dist
+    from cymf_b200 import _lib
+    from cymf_b200.wmf import AlsSession
+    from cymf_b200.host import init_factors
+    W, H = init_factors(train.shape[0], train.shape[1], K)
+    s = AlsSession(train, W, H, ALS_WD, ALS_WEIGHT, dtype="float32", cg_tol=1e-6, cg_max_iter=2 * K,
+                   distributed=world > 1)
+    for _ in range(warmup):
+        s.epoch()
+    sync_all()
+    it0 = s.stats()[0]
+    l0 = _lib.launch_count()
+    s.kernel_events = []
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
+    for t in range(steps):
+        s.epoch()
+        evs[t + 1].record()
+    sync_all()
+    launches = _lib.launch_count() - l0
+    kev, s.kernel_events = s.kernel_events, None
+    per_step = [evs[t].elapsed_time(evs[t + 1]) * 1e-3 for t in range(steps)]
+    k_bytes = float(sum(b for b, _, _ in kev))
+    k_sec = float(sum(e0.elapsed_time(e1) for _, e0, e1 in kev)) * 1e-3
+    t = torch.tensor([sum(per_step), k_sec], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs_all = float(t[0])
+    iters = s.stats()[0] - it0
+    # parity scalar: one more epoch, each half sweep checked right after it ran (the other side is still the one it
+    # was solved against)
+    s.user_half()
+    ru = s.residual("user", 24, seed=1000 + s.rank)
+    s.item_half()
+    ri = s.residual("item", 24, seed=2000 + s.rank)
+    r = torch.tensor([ru, ri], dtype=torch.float64, device="cuda")
+    fin = torch.tensor([float(torch.isfinite(s.dW).all() and torch.isfinite(s.dH).all())], device="cuda")
+    if world > 1:
+        dist.all_reduce(r, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fin, op=dist.ReduceOp.MIN)
+    rows = train.shape[0] + train.shape[1]
+    out = {"secs_all": secs_all, "per_step": per_step, "launches": launches,
+           "kernel_bytes_per_launch": k_bytes / max(len(kev), 1), "kernel_sec_per_launch": float(t[1]) / max(len(kev), 1),
+           "kernel_launches": len(kev), "bytes_per_epoch": s.bytes_per_epoch,
+           "cg_iterations_per_row": iters * world / (steps * rows), "unconverged_rows": s.stats()[1],
+           "gather": "peer-store (fused into the GEMM epilogue)" if s.peer else ("nccl all-gather" if s.dist else "single"),
+           "row_solver": s.row_solver, "peer_error": s.peer_error,
+           "parity": {"rel_residual": float(r.max()), "user_rows": float(r[0]), "item_rows": float(r[1]),
+                      "rows_checked_per_side_per_rank": 25, "factors_finite": bool(fin.item() > 0),
+                      "what": "max over ranks of |A x - b| / |b| in float64 for the reference's per-row system "
+                              "(cymf/wmf.pyx:161-168) on 24 random rows + the heaviest row of each rank's block, "
+                              "user rows after a user half sweep, item rows after an item half sweep; bar 1e-4"}}
+    del s
+    torch.cuda.empty_cache()
+    return out
+
+
+def time_als_e2e(train, K, steps, warmup, sync_all, world):
+    """`cymf_b200.WMF(K).fit(X, 1)` per step with pinned HOST buffers: CSR + both f64 factor matrices go up, the
+    device prepares X^T / the row deal / the blocks, one epoch runs, both factor matrices come back."""
+    import torch
+    import torch.distributed as dist
+    import cymf_b200 as cymf
+    from cymf_b200.host import init_factors
+    from scipy import sparse
+
+    def pinned(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+    X = sparse.csr_matrix((pinned(train.data.astype(np.float64)), pinned(train.indices), pinned(train.indptr)),
+                          shape=train.shape, copy=False)
+    X.has_sorted_indices = True
+    m = cymf.WMF(K, ALS_WD, ALS_WEIGHT, distributed=world > 1)
+    m.W, m.H = (pinned(a) for a in init_factors(train.shape[0], train.shape[1], K))
+    for _ in range(max(1, min(warmup, 2))):
+        m.fit(X, 1, 1, verbose=False)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.fit(X, 1, 1, verbose=False)
+    sync_all()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    h2d, d2h = m.transfer_bytes_
+    return float(dt[0]), int(h2d), int(d2h)
+
+
+def bpr_block(train, users, positives, K, opt, dt, steps, hbm, traffic=None):
+    """One BPR configuration, device-resident, with its own roofline block."""
+    import torch
+    s_, a_, ss, ps = time_bpr_device(train, users, positives, K, opt, steps, 3, dtype=dt)
+    bpu = ss.bytes_per_update
+    gbps = a_ * bpu / s_ / 1e9
+    out = {"updates_per_s": a_ / s_, "ms_per_epoch": 1e3 * s_ / len(ps), "K": K, "optimizer": opt, "dtype": dt,
+           "acceptance": a_ / (len(ps) * users.shape[0]),
+           "roofline": {"bound": "hbm", "achieved": gbps, "peak": hbm, "unit": "GB/s", "frac": gbps / hbm,
+                        "bytes_per_update": bpu, "traffic": traffic}}
+    del ss
+    torch.cuda.empty_cache()
+    return out
+
+
+def time_c1():
+    """BASELINE configs[0]: BPR K=20 lr=0.01 wd=0.01, 30 epochs on the ml-100k shape through the public `fit()`
+    (wall clock, everything included), in epochs/s next to the reference README's 98.46 it/s (README.md:62-66)."""
+    import cymf_b200 as cymf
+    train, _ = cymf.synth.movielens_like("ml-100k")
+    out = {}
+    for opt in ("adam", "sgd"):
+        m = cymf.BPR(20, 0.01, opt, 0.01)
+        m.fit(train, 2, 8, verbose=False)                     # library / allocator warm-up
+        t0 = time.perf_counter()
+        m = cymf.BPR(20, 0.01, opt, 0.01)
+        m.fit(train, 30, 8, verbose=False)
+        dt = time.perf_counter() - t0
+        out[opt] = {"epochs_per_s_incl_setup": 30 / dt, "sec_for_30_epochs": dt}
+    out["reference_readme_it_per_s"] = 98.46
+    out["note"] = "reference figure: real ml-100k, Adam, 8 threads, unstated hardware (README.md:66); context only"
+    return out
 
 
 def main():
@@ -473,7 +674,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--full", action="store_true", help="GloVe extra at the full 1e8 co-occurrences of configs[3]")
+    ap.add_argument("--glove-samples", type=int, default=100_000_000, help="co-occurrences of the GloVe extra (configs[3]: 1e8)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
     if args.impl == "reference":
@@ -481,7 +682,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from cymf_b200 import _lib
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -500,100 +700,106 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    launches0 = _lib.launch_count()
     sampler = ClockSampler(local)
     sampler.start()
     sync_all()
-    secs, applied, sess, per_step = time_bpr_device(train, users, positives, K_MAIN, "sgd", args.steps, args.warmup)
+    main_res = time_als_main(train, K_MAIN, args.steps, args.warmup, sync_all, world, hbm)
     sync_all()
     clocks = sampler.stop()
-    launches = sess.timed_launches
-    stats = torch.tensor([secs, float(applied)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = stats.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-        secs_all, applied_all = float(tmax[0]), float(stats[1])
-    else:
-        secs_all, applied_all = secs, float(applied)
-    value = applied_all / secs_all
-    bpu = sess.bytes_per_update
-    kernel_s = float(np.mean(per_step))
-    achieved = (applied / args.steps) * bpu / kernel_s / 1e9
-    del sess
-    torch.cuda.empty_cache()
+    secs_all = main_res["secs_all"]
+    value = args.steps / secs_all
+    k_gbps = main_res["kernel_bytes_per_launch"] / max(main_res["kernel_sec_per_launch"], 1e-12) / 1e9
 
-    # end-to-end through the typed boundary with host buffers
     e_steps = max(2, min(args.steps, 5))
-    sync_all()
-    e_secs, e_applied, h2d, d2h = time_bpr_e2e(train, users, positives, K_MAIN, "sgd", e_steps, args.warmup)
-    e = torch.tensor([e_secs, float(e_applied)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        emax = e.clone()
-        dist.all_reduce(emax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e, op=dist.ReduceOp.SUM)
-        e_value = float(e[1]) / float(emax[0])
-    else:
-        e_value = e_applied / e_secs
+    e_secs, h2d, d2h = time_als_e2e(train, K_MAIN, e_steps, args.warmup, sync_all, world)
+
+    def guarded(tag, fn):
+        try:
+            extra[tag] = fn()
+        except Exception as ex:                              # noqa: BLE001 - an extra must never cost the headline line
+            extra[tag] = {"failed": repr(ex)}
+        torch.cuda.empty_cache()
 
     extra = {}
-    if rank == 0 and not args.no_extra:
-        for tag, K, opt, dt in (("bpr_sgd_f32_k64", 64, "sgd", "float32"), ("bpr_adam_f32_k128", 128, "adam", "float32"),
-                                ("bpr_sgd_f64_k128", 128, "sgd", "float64")):
-            s_, a_, ss, ps = time_bpr_device(train, users, positives, K, opt, max(3, args.steps // 2), 3, dtype=dt)
-            extra[tag] = {"updates_per_s": a_ / s_, "ms_per_epoch": 1e3 * s_ / len(ps),
-                          "algorithmic_GBps": a_ * ss.bytes_per_update / s_ / 1e9,
-                          "frac_of_hbm_peak": a_ * ss.bytes_per_update / s_ / 1e9 / hbm}
-            del ss
-            torch.cuda.empty_cache()
-        extra["wmf_als_f32_k128_c5_scale0.1"] = time_als_device_pipeline(0.1, 128, 3, hbm)
-        extra["evaluator_ml20m_k128"] = time_evaluator("ml-20m", 128, 3, hbm, with_reference=(world == 1 and not args.no_cpu))
-        for tag, opt in (("relmf_sgd_f32_k128", "sgd"), ("relmf_adam_f32_k128", "adam")):
-            extra[tag] = time_relmf_device(train, 128, opt, max(3, args.steps // 2), 3, hbm, 50_000_000)
-            torch.cuda.empty_cache()
+    x_steps = max(3, args.steps // 2)
     if not args.no_extra:
-        # WMF ALS shards over the ranks (row blocks, all-gather + Gram all-reduce): every rank takes part
-        for tag, name, K in (("wmf_als_f32_k64_ml1m", "ml-1m", 64), ("wmf_als_f32_k128_ml20m", "ml-20m", 128)):
+        # sharded over the ranks like the headline: every rank takes part
+        for tag, name, K in (("wmf_als_f32_k64_ml1m_c2", "ml-1m", 64),):
             if rank == 0:
                 dataset(name)
             sync_all()
-            res = time_als(dataset(name)[0], K, "float32", max(3, args.steps // 2), 3, sync_all, world, hbm)
+            res = time_als(dataset(name)[0], K, "float32", x_steps, 3, sync_all, world, hbm)
             if rank == 0:
                 extra[tag] = res
-        if rank == 0:
-            extra["glove_adagrad_f32_k300"] = time_glove(400_000, 100_000_000 if args.full else 20_000_000, 300,
-                                                         max(3, args.steps // 2), 3, hbm)
+        if world > 1:
+            # BASELINE configs[4] at FULL size (10 M x 1 M x ~1 B nnz, generated on the device), sharded
+            try:
+                res = time_als_device_pipeline(1.0, 128, 2, hbm, world, sync_all)
+            except Exception as ex:                          # noqa: BLE001
+                res = {"failed": repr(ex)}
+            if rank == 0:
+                extra["wmf_als_f32_k128_c5_full"] = res
+    if rank == 0 and not args.no_extra:
+        # BPR: the other half of BASELINE.json's metric (configs[2] and the K=64 target run), one GPU
+        guarded("bpr_sgd_f32_k128_c3", lambda: bpr_block(train, users, positives, 128, "sgd", "float32", x_steps, hbm,
+                                                        traffic={"bytes_per_launch": 13.156e9,
+                                                                 "source": "profiles/r1_bpr_hogwild_k128_ncu_full.txt"}))
+        guarded("bpr_sgd_f32_k64", lambda: bpr_block(train, users, positives, 64, "sgd", "float32", x_steps, hbm))
+        guarded("bpr_adam_f32_k128", lambda: bpr_block(train, users, positives, 128, "adam", "float32", x_steps, hbm))
+        guarded("bpr_sgd_f64_k128", lambda: bpr_block(train, users, positives, 128, "sgd", "float64", x_steps, hbm))
+        guarded("bpr_sgd_f64_k64", lambda: bpr_block(train, users, positives, 64, "sgd", "float64", x_steps, hbm))
+
+        def bpr_e2e(dtype):
+            e_s, e_a, bh2d, bd2h = time_bpr_e2e(train, users, positives, K_MAIN, "sgd", 3, 2, dtype=dtype)
+            return {"updates_per_s": e_a / e_s, "h2d_bytes_per_step": int(bh2d), "d2h_bytes_per_step": int(bd2h),
+                    "call": f"cymf_b200.BPR(dtype={dtype!r})._fit_bpr(users, positives, X, 1, lr, wd, 1, False)"}
+        guarded("bpr_e2e_f32_k128", lambda: bpr_e2e("float32"))
+        guarded("bpr_e2e_f64_k128", lambda: bpr_e2e("float64"))
+        guarded("bpr_c1_ml100k_k20_30_epochs", time_c1)
+        if world == 1:
+            guarded("wmf_als_f32_k128_c5_scale0.1", lambda: time_als_device_pipeline(0.1, 128, 3, hbm, 1, sync_all))
+        guarded("evaluator_ml20m_k128", lambda: time_evaluator("ml-20m", 128, 3, hbm,
+                                                               with_reference=(world == 1 and not args.no_cpu)))
+        for tag, opt in (("relmf_sgd_f32_k128", "sgd"), ("relmf_adam_f32_k128", "adam")):
+            guarded(tag, lambda opt=opt: time_relmf_device(train, 128, opt, x_steps, 3, hbm, 50_000_000))
+        guarded("glove_adagrad_f32_k300_c4", lambda: time_glove(400_000, args.glove_samples, 300, x_steps, 3, hbm))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            cpu = cpu_reference_bpr(train, users, positives, K_MAIN, "sgd")
+            cpu = cpu_reference_als(train, K_MAIN, 3, 1)
         except Exception as ex:                                      # the checker is optional for the GPU number
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
-
-    if cpu is not None and not args.no_extra:
-        extra["cpu_reference"] = cpu_reference_extras()
+        if not args.no_extra:
+            try:
+                extra["cpu_reference"] = cpu_reference_extras()
+                extra["cpu_reference"]["bpr_sgd_k128_c3"] = cpu_reference_bpr(train, users, positives, K_MAIN, "sgd")
+            except Exception as ex:                                  # noqa: BLE001
+                extra["cpu_reference"] = {"failed": repr(ex)}
     if rank == 0:
+        frac = k_gbps / hbm
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * secs_all / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "optimizer": "sgd", "learning_rate": LR, "weight_decay": WD,
-                           "pairs_per_epoch": int(users.shape[0]), "acceptance": applied / (args.steps * users.shape[0]),
-                           "multi_gpu": "replicas only (BPR does not shard)" if world > 1 else "single GPU",
-                           "l2": "inputs larger than L2: 144 MB of pairs are streamed per step next to 85 MB of "
-                                 "factors (L2 = 126 MB); no explicit flush"},
+                "warmup": args.warmup, "ms_per_step": 1e3 * secs_all / args.steps, "sec_per_epoch": secs_all / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_block(world),
+                "parity": main_res["parity"],
                 "clocks": clocks,
-                "e2e": {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e_steps, "call": "cymf_b200.BPR._fit_bpr(users, positives, X, 1, lr, wd, 1, False)"},
-                "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                             # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
-                             # command (profiles/r1_bpr_hogwild_k128_ncu_full.txt): 9.274 GB + 3.882 GB
-                             "traffic": 13.156e9, "traffic_unit": "bytes/launch",
-                             "algorithmic_bytes_per_launch": (applied / args.steps) * bpu,
-                             "peak_source": peak_src, "kernel": "bpr_hogwild_kernel<float,SGD,32,1,RED>",
-                             "bytes_per_update": bpu,
-                             "note": "factors (85 MB) fit the 126 MB L2, so algorithmic bytes/s may exceed DRAM bytes/s"},
+                "e2e": {"value": e_steps / e_secs, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e_steps, "call": "cymf_b200.WMF(128, 0.01, 10.0).fit(X, 1, 1, verbose=False), warm-started"},
+                "gpu_launches": int(main_res["launches"]),
+                "roofline": {"bound": "hbm", "achieved": k_gbps, "peak": hbm * 1.0, "unit": "GB/s", "frac": frac,
+                             "traffic": ROOFLINE_TRAFFIC, "traffic_unit": "bytes/launch",
+                             "algorithmic_bytes_per_launch": main_res["kernel_bytes_per_launch"],
+                             "sec_per_launch": main_res["kernel_sec_per_launch"],
+                             "launches_timed": main_res["kernel_launches"],
+                             "peak_source": peak_src, "kernel": "tc::als_rows_tc_kernel<128>",
+                             "per_gpu": "max-over-ranks kernel time against one GPU's peak: each rank moves its own block",
+                             "epoch_algorithmic_GBps_all_gpus": main_res["bytes_per_epoch"] * args.steps / secs_all / 1e9,
+                             "epoch_frac_of_aggregate_peak": main_res["bytes_per_epoch"] * args.steps / secs_all / 1e9 / (hbm * world),
+                             "note": "the fixed side (<= 71 MB) fits the 126 MB L2 at this shape, so algorithmic bytes/s "
+                                     "may exceed DRAM bytes/s"},
+                "als": {k: main_res[k] for k in ("cg_iterations_per_row", "unconverged_rows", "gather", "row_solver",
+                                                 "peer_error")},
                 "cpu_baseline": cpu, "extra": extra}
         print(json.dumps(line))
     if world > 1:

@@ -79,6 +79,7 @@ SIGNATURES = {
     "cymf_gram_workspace_doubles": (_i64, [_i64, _i32]),
     "cymf_gram_dev": (C.c_int, [_p, C.c_int, _i64, _i32, _i32, _f64, C.c_int, _p, _i64, _p, _p, _p]),
     "cymf_gram_finalize_dev": (C.c_int, [_p, C.c_int, _i32, _i32, _f64, _p, _p]),
+    "cymf_gram_sum_dev": (C.c_int, [C.POINTER(_p), _i32, _i32, _f64, _p, _p]),
     "cymf_als_cg_dev": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, C.c_int, _i32, _i32, _f64, _f64, _i32, _i32, _i32,
                                   _p, _p, _p]),
     "cymf_als_rows_tc_dev": (C.c_int, [_p, _p, _p, _i32, _p, _p, C.c_int, _i32, _i32, _f64, _f64, _i32, _p, _p, _p]),

@@ -735,6 +735,30 @@ extern "C" int cymf_gram_finalize_dev(const double *in_f64, int dtype, int32_t K
     return 0;
 }
 
+// Cross-rank sum of Gram partials: out64 = sum_r parts[r] (+ wd on the diagonal), ranks in index order on every rank
+// (so all ranks hold bit-identical G).  parts[r] may be NVLink peer memory (symmetric buffers): this is the Gram
+// all-reduce of the sharded half sweep done with plain peer loads instead of a latency-bound NCCL call.
+struct GramParts { const double *p[8]; int n; };
+__global__ void gram_sum_kernel(const GramParts parts, int KK, int K, double wd, double *__restrict__ out64) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= KK) return;
+    double s = 0.0;
+    for (int r = 0; r < parts.n; ++r) s += parts.p[r][t];
+    if (t / K == t % K) s += wd;
+    out64[t] = s;
+}
+
+extern "C" int cymf_gram_sum_dev(const double *const *parts, int32_t n_parts, int32_t K, double weight_decay,
+                                 double *out_f64, void *stream) {
+    CYMF_REQUIRE(parts && out_f64 && n_parts >= 1 && n_parts <= 8 && K > 0 && K <= 128, "bad argument");
+    GramParts gp{};
+    gp.n = n_parts;
+    for (int r = 0; r < n_parts; ++r) { CYMF_REQUIRE(parts[r] != nullptr, "null partial"); gp.p[r] = parts[r]; }
+    gram_sum_kernel<<<(K * K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gp, K * K, K, weight_decay, out_f64);
+    CYMF_LAUNCHED();
+    return 0;
+}
+
 // In-place Gauss-Jordan inversion of a symmetric positive definite K x K matrix (f64, one CTA, matrix in shared
 // memory; no pivoting is needed for SPD input).  Output [ld, ld] of T, zero padded.
 template <typename T>

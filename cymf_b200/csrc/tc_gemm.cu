@@ -127,9 +127,9 @@ struct GatherPlan {
 };
 
 template <bool GATHER>
-__global__ void __launch_bounds__(128) tc_gram_partial_kernel(const float *__restrict__ Y, int64_t n, int K, int ld,
-                                                              double *__restrict__ partial, uint32_t tmem_cols,
-                                                              const GatherPlan plan) {
+__global__ void __launch_bounds__(128) tc_gram_partial_kernel(const float *__restrict__ Y, int64_t n, int64_t slab_rows,
+                                                              int K, int ld, double *__restrict__ partial,
+                                                              uint32_t tmem_cols, const GatherPlan plan) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *t_hi = reinterpret_cast<float *>(smem_raw);            // [TILE_M x 32]: operand rows = columns of Y (zero past ld)
     float *t_lo = t_hi + TILE_M * CHUNK_K;
@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(128) tc_gram_partial_kernel(const float *__res
         r1 = r0 + TC_GRAM_SLAB < end ? r0 + TC_GRAM_SLAB : end;
         gidx = plan.indices;
     } else {
-        r0 = (int64_t)blockIdx.x * TC_GRAM_SLAB;
-        r1 = r0 + TC_GRAM_SLAB < n ? r0 + TC_GRAM_SLAB : n;
+        r0 = (int64_t)blockIdx.x * slab_rows;                    // a multiple of 32 rows per CTA
+        r1 = r0 + slab_rows < n ? r0 + slab_rows : n;
     }
     double colsum = 0.0;
     uint32_t phase = 0;
@@ -241,15 +241,23 @@ int tc_rows_times_matrix(const float *in, float *const *outs, int n_outs, const 
     return 0;
 }
 
-int64_t tc_gram_slabs(int64_t n) { return (n + tc::TC_GRAM_SLAB - 1) / tc::TC_GRAM_SLAB; }
+// Rows of Y per Gram CTA: at least 512; for long matrices whatever spreads them over two CTAs per SM, so that the
+// number of K x K partials (and the serial sum over them in gram_finish_kernel: 19.5 k partials = 2.5 GB at 10 M
+// rows before) stays below ~300 whatever n is.  Depends on n and the SM count only: deterministic.
+static int64_t tc_gram_slab_rows(int64_t n) {
+    const int64_t ctas = 2 * (int64_t)sm_count();
+    int64_t rows = ((n + ctas - 1) / ctas + 31) / 32 * 32;
+    return rows < tc::TC_GRAM_SLAB ? tc::TC_GRAM_SLAB : rows;
+}
+int64_t tc_gram_slabs(int64_t n) { const int64_t r = tc_gram_slab_rows(n); return (n + r - 1) / r; }
 
 int tc_gram_partial(const float *Y, int64_t n, int K, int ld, double *partial, cudaStream_t st) {
     const int64_t slabs = tc_gram_slabs(n);
     if (slabs == 0) return 0;
     const size_t smem = sizeof(float) * (size_t)(2 * tc::TILE_M * tc::CHUNK_K) + sizeof(double) * (size_t)ld * tc::TILE_M;
     CYMF_CUDA(cudaFuncSetAttribute(tc::tc_gram_partial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc::tc_gram_partial_kernel<false><<<(unsigned)slabs, 128, smem, st>>>(Y, n, K, ld, partial, tc::tmem_columns(ld, 1),
-                                                                         tc::GatherPlan{});
+    tc::tc_gram_partial_kernel<false><<<(unsigned)slabs, 128, smem, st>>>(Y, n, tc_gram_slab_rows(n), K, ld, partial,
+                                                                         tc::tmem_columns(ld, 1), tc::GatherPlan{});
     CYMF_LAUNCHED();
     return 0;
 }
@@ -262,7 +270,7 @@ int tc_gram_gather(const float *Y, const int64_t *indptr, const int32_t *indices
     const size_t smem = sizeof(float) * (size_t)(2 * tc::TILE_M * tc::CHUNK_K) + sizeof(double) * (size_t)ld * tc::TILE_M;
     CYMF_CUDA(cudaFuncSetAttribute(tc::tc_gram_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc::GatherPlan plan{indptr, indices, order, first_slab, n_heavy, bsum};
-    tc::tc_gram_partial_kernel<true><<<(unsigned)n_slabs, 128, smem, st>>>(Y, 0, K, ld, partial, tc::tmem_columns(ld, 1), plan);
+    tc::tc_gram_partial_kernel<true><<<(unsigned)n_slabs, 128, smem, st>>>(Y, 0, 0, K, ld, partial, tc::tmem_columns(ld, 1), plan);
     CYMF_LAUNCHED();
     return 0;
 }

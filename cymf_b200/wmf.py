@@ -38,7 +38,7 @@ class WMF(object):
     """
 
     def __init__(self, num_components=20, weight_decay=0.01, weight=10.0, *, dtype="float32", cg_tol=None,
-                 cg_max_iter=None, device=None, distributed="auto", peer_gather=True, solver="transformed",
+                 cg_max_iter=None, device=None, distributed=False, peer_gather=True, solver="transformed",
                  prep="device", heavy_min=4096):
         self.num_components = int(num_components)
         self.weight_decay = float(weight_decay)
@@ -110,8 +110,10 @@ class WMF(object):
                           heavy_min=self.heavy_min)
         # how solved blocks reach the other ranks: "single" | "peer-store" (fused into the GEMM epilogue) | "nccl"
         self.gather_mode_ = "peer-store" if sess.peer else ("nccl" if sess.dist else "single")
+        self.row_solver_ = sess.row_solver
         run_epochs(self, sess, num_epochs, sess.epoch, verbose, ncols=100)
         self.cg_iterations_, self.cg_unconverged_ = sess.stats()
+        self.transfer_bytes_ = (sess.h2d_bytes, sess.d2h_bytes)     # host<->device bytes this fit moved
 
     def _als(self, indptr, indices, X, Y, num_threads=1):
         """`WMF._als(indptr, indices, X, Y, num_threads)` (wmf.pyx:136): solves every row of the HOST array X in
@@ -158,11 +160,15 @@ class AlsSession(object):
     replicas of W and H in dealt order); `epoch()` = user half sweep + item half sweep (wmf.pyx:111-112)."""
 
     def __init__(self, X, W, H, weight_decay, weight, *, K=None, dtype="float32", cg_tol=1e-6, cg_max_iter=128, device=None,
-                 distributed="auto", stage_rows=0, force_width=0, solver="transformed", peer_gather=True,
+                 distributed=False, stage_rows=0, force_width=0, solver="transformed", peer_gather=True,
                  prep="device", overlap_classes=True, heavy_min=4096):
         torch = _lib.require_cuda()
         self.heavy_min = int(heavy_min)
         self.tail_divisor = int(os.environ.get("CYMF_ALS_TAIL_DIVISOR", "256"))     # tuning hook (tools/c5_als.py)
+        # rows of at most this many entries go to the streaming CG kernel even when the tensor-core solver is on: its
+        # cost grows with the row length (~145 SM-clocks per entry) while the one-pass solver pays ~10 k SM-clocks per
+        # row whatever its length (K x K CG from registers), so very short rows are cheaper streamed.  0 = never.
+        self.short_max = int(os.environ.get("CYMF_ALS_SHORT", "0"))
         self.peer_error = None
         self._unperm = {}
         self.force_width = int(force_width)
@@ -171,6 +177,9 @@ class AlsSession(object):
         self.solver = solver
         import torch.distributed as dist
         self._L = _lib.lib()
+        # distributed=True: `fit` is a COLLECTIVE over the default process group -- every rank must call it with the
+        # same X (the reference has no multi-device mode).  The default (False) keeps a process that
+        # uses torch.distributed for something else -- e.g. independent per-rank fits -- free of hidden collectives.
         self.dist = dist if (distributed in ("auto", True) and dist.is_available() and dist.is_initialized()
                              and dist.get_world_size() > 1) else None
         self.world = self.dist.get_world_size() if self.dist else 1
@@ -190,7 +199,7 @@ class AlsSession(object):
         self.wd, self.weight = float(weight_decay), float(weight)
         self.cg_tol, self.cg_max_iter, self.stage_rows = float(cg_tol), int(cg_max_iter), int(stage_rows)
         self.prep = prep
-        self._side, self.overlap_classes = None, bool(overlap_classes)
+        self.overlap_classes = bool(overlap_classes)
         with torch.cuda.device(dev):
             if prep == "device":
                 blk_u, blk_i = self._prepare_on_device(X)
@@ -208,23 +217,34 @@ class AlsSession(object):
             self.order_i = torch.arange(self.Ri, dtype=torch.int32, device=dev)
             self.dW = self._upload(W, self.slot_u)
             self.dH = self._upload(H, self.slot_i)
-            # Multi-GPU: put both replicas in NVLink-mapped symmetric memory so that the back-transform GEMM can
-            # write each solved row into every rank's replica (GEMM + all-gather in one kernel).  If symmetric
-            # memory cannot be set up the blocks are exchanged with NCCL all_gather_into_tensor instead.
-            self.peer = None
-            if self.dist and peer_gather and self.solver == "transformed":
-                self.peer = self._make_symmetric()
             nws = int(self._L.cymf_gram_workspace_doubles(max(Up, Ip), K))
             self.ws = torch.empty(max(nws, 1), dtype=torch.float64, device=dev)
             self.g64 = torch.empty(K * K, dtype=torch.float64, device=dev)
             self.G = torch.empty(ld * ld, dtype=tdt, device=dev)       # [ld, ld], zero padded
             self.Ginv = torch.empty(ld * ld, dtype=tdt, device=dev)
             self.By, self.Bfwd, self.Bbwd = (torch.empty(ld * ld, dtype=tdt, device=dev) for _ in range(3))
-            self.Yt = torch.empty((max(Up, Ip), ld), dtype=tdt, device=dev)     # fixed side in transformed coordinates
             self.queue = torch.zeros(4, dtype=torch.int32, device=dev)     # one work-queue head per row class
             self.d_stats = torch.zeros(2, dtype=torch.int64, device=dev)
             self.d_info = torch.zeros(1, dtype=torch.int32, device=dev)    # Cholesky pivot failures (checked in stats())
+            # Transformed solver: every rank keeps the WHOLE fixed side in the coordinates y~ = L^-1 y (Yt["item"] is the
+            # item factors as the user half sweep reads them, Yt["user"] the user factors for the item half sweep) and
+            # its own block of each factor matrix in the original coordinates.  After a half sweep the solved block is
+            # transformed for the NEXT half sweep and written into all ranks' Yt straight from the GEMM epilogue
+            # (NVLink peer stores into symmetric memory): the all-gather of SURVEY.md 8(e) moves y~ instead of y, so no
+            # rank ever transforms rows it does not own.  The K x K Gram partials meet in a symmetric buffer too.
+            self.Yt = {"user": torch.zeros((Up, ld), dtype=tdt, device=dev),
+                       "item": torch.zeros((Ip, ld), dtype=tdt, device=dev)}
+            self.gpart = torch.zeros(K * K, dtype=torch.float64, device=dev)
+            self.peer = None
+            if self.dist and peer_gather and self.solver == "transformed":
+                self.peer = self._make_symmetric()
+            self._stale = {"user": False, "item": False}      # other ranks' blocks of dW / dH are out of date
+            self._pub_side = None                             # side whose Yt / transforms were published last
+            self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+            self._graph, self.graph_error = None, None
+            self.use_graph = os.environ.get("CYMF_ALS_GRAPH", "1") == "1"
         self.epochs_done = 0
+        self.kernel_events = None        # set to [] to record (algorithmic bytes, start, end) CUDA events per row-solver launch
         self.h2d_bytes = self._nbytes(W) + self._nbytes(H) + 8 * (self.Ru + self.Ri + 2) + 4 * sum(self.block_nnz)
         self.d2h_bytes = self._nbytes(W) + self._nbytes(H)
 
@@ -285,18 +305,18 @@ class AlsSession(object):
         return blk_u, blk_i
 
     def _make_symmetric(self):
-        """Move dW / dH into symmetric memory; returns {id(tensor): (handle, [peer base pointers])} or None."""
+        """Move Yt["user"], Yt["item"] and the Gram partial into NVLink-mapped symmetric memory.  Returns
+        {name: (handle, [base pointer of every rank's copy])} or None (then NCCL collectives carry the exchange)."""
         import torch
+        moved = []
         try:
             import torch.distributed._symmetric_memory as symm
             group = self.dist.group.WORLD
-            out = {}
-            moved = []
-            for name in ("dW", "dH"):
-                old = getattr(self, name)
+            gname = group.group_name if hasattr(group, "group_name") else group
+            for name, old in (("user", self.Yt["user"]), ("item", self.Yt["item"]), ("gram", self.gpart)):
                 new = symm.empty(tuple(old.shape), dtype=old.dtype, device=self.dev)
                 new.copy_(old)
-                hdl = symm.rendezvous(new, group.group_name if hasattr(group, "group_name") else group)
+                hdl = symm.rendezvous(new, gname)
                 ptrs = [int(p) for p in hdl.buffer_ptrs]
                 if len(ptrs) != self.world or ptrs[self.rank] != new.data_ptr():
                     raise RuntimeError("unexpected symmetric-memory layout")
@@ -306,15 +326,18 @@ class AlsSession(object):
             import warnings
             self.peer_error = repr(exc)
             warnings.warn(f"cymf_b200.WMF: symmetric (NVLink peer) memory unavailable, blocks are exchanged with NCCL "
-                          f"all-gather instead: {self.peer_error}", RuntimeWarning)
+                          f"collectives instead: {self.peer_error}", RuntimeWarning)
             ok = torch.zeros(1, device=self.dev)
-            moved = []
         self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)        # all ranks take the same path
         if ok.item() < 1:
             return None
+        out = {}
         for name, new, hdl, ptrs in moved:
-            setattr(self, name, new)
-            out[new.data_ptr()] = (hdl, ptrs)
+            if name == "gram":
+                self.gpart = new
+            else:
+                self.Yt[name] = new
+            out[name] = (hdl, ptrs)
         return out
 
     def _upload(self, host, slots):
@@ -364,60 +387,82 @@ class AlsSession(object):
             if nh:
                 first = np.concatenate([[0], np.cumsum((lengths[:nh] + 511) // 512)]).astype(np.int32)
                 heavy = (nh, first, torch.from_numpy(first).to(self.dev))
+        self._n_long = getattr(self, "_n_long", {})
+        self._n_long[id(blk_indptr)] = int((lengths > self.short_max).sum()) if self.short_max > 0 else n
         return (max(b16 - nh, 0), max(b8 - max(nh, b16), 0), n - max(nh, b8)), heavy
 
-    def _half(self, X_full, R, csr, order, Y_full, Ry, classes, heavy):
-        import torch
+    def _side(self, side):
+        if side == "user":
+            return self.dW, self.Ru, self.csr_u, self.order_u, self.classes_u, self.heavy_u, "item"
+        return self.dH, self.Ri, self.csr_i, self.order_i, self.classes_i, self.heavy_i, "user"
+
+    def _publish(self, side):
+        """This rank's block of `side`'s factor matrix has just been solved (original coordinates).  Make it the
+        fixed side of the next half sweep: G = X^T X + wd I (wmf.pyx:142-143) from the ranks' K x K partials,
+        G = L L^T, and X~ = X L^-T for this rank's rows written into EVERY rank's Yt[side]."""
         L, K, ld = self._L, self.K, self.ld
+        X_full, R = self._side(side)[:2]
+        x_blk = X_full[self.rank * R:(self.rank + 1) * R]
         stream = _lib.stream_ptr()
         es = 4 if self.dtype == _lib.F32 else 8
-        if self.dist:
-            # Gram partial over this rank's block of Y, all-reduced over NVLink, then + wd I  (wmf.pyx:142-143)
-            y_blk = Y_full[self.rank * Ry:(self.rank + 1) * Ry]
-            _lib.check(L.cymf_gram_dev(_lib.ptr(y_blk), self.dtype, Ry, K, ld, self.wd, 0, _lib.ptr(self.ws),
+        if not self.dist:
+            _lib.check(L.cymf_gram_dev(_lib.ptr(x_blk), self.dtype, R, K, ld, self.wd, 1, _lib.ptr(self.ws),
                                        self.ws.numel(), _lib.ptr(self.g64), None, stream))
-            self.dist.all_reduce(self.g64)
-            _lib.check(L.cymf_gram_finalize_dev(_lib.ptr(self.g64), self.dtype, K, ld, self.wd, _lib.ptr(self.G), stream))
-            add_diag = self.wd                                   # g64 holds the all-reduced Y^T Y without wd I
         else:
-            _lib.check(L.cymf_gram_dev(_lib.ptr(Y_full), self.dtype, Y_full.shape[0], K, ld, self.wd, 1,
-                                       _lib.ptr(self.ws), self.ws.numel(), _lib.ptr(self.g64), _lib.ptr(self.G), stream))
-            add_diag = 0.0
+            _lib.check(L.cymf_gram_dev(_lib.ptr(x_blk), self.dtype, R, K, ld, self.wd, 0, _lib.ptr(self.ws),
+                                       self.ws.numel(), _lib.ptr(self.gpart), None, stream))
+            if self.peer is not None:
+                # Gram all-reduce as peer loads: barrier (all partials written), every rank sums them in rank order
+                hdl, ptrs = self.peer["gram"]
+                hdl.barrier(channel=0)
+                parts = (C.c_void_p * self.world)(*ptrs)
+                _lib.check(L.cymf_gram_sum_dev(parts, self.world, K, self.wd, _lib.ptr(self.g64), stream))
+            else:
+                self.dist.all_reduce(self.gpart)
+                parts = (C.c_void_p * 1)(self.gpart.data_ptr())
+                _lib.check(L.cymf_gram_sum_dev(parts, 1, K, self.wd, _lib.ptr(self.g64), stream))
+        _lib.check(L.cymf_chol_transforms_dev(_lib.ptr(self.g64), K, ld, 0.0, self.dtype, _lib.ptr(self.By),
+                                              _lib.ptr(self.Bfwd), _lib.ptr(self.Bbwd), _lib.ptr(self.d_info), stream))
+        yt = self.Yt[side]
+        off = self.rank * R * ld * es
+        if self.peer is not None:
+            hdl, ptrs = self.peer[side]
+            outs = (C.c_void_p * self.world)(*[p + off for p in ptrs])
+            _lib.check(L.cymf_rows_times_matrix_multi_dev(_lib.ptr(x_blk), outs, self.world, _lib.ptr(self.By),
+                                                          self.dtype, R, ld, stream))
+            hdl.barrier(channel=0)                               # every rank's rows have landed in this rank's Yt
+        else:
+            y_blk = yt[self.rank * R:(self.rank + 1) * R]
+            _lib.check(L.cymf_rows_times_matrix_dev(_lib.ptr(x_blk), _lib.ptr(y_blk), _lib.ptr(self.By), self.dtype,
+                                                    R, ld, stream))
+            if self.dist:
+                self.dist.all_gather_into_tensor(yt, y_blk)
+
+    def _solve(self, side):
+        """Solve this rank's block of `side` against the published fixed side (wmf.pyx:150-168)."""
+        import torch
+        L, K, ld = self._L, self.K, self.ld
+        X_full, R, csr, order, classes, heavy, other = self._side(side)
         x_blk = X_full[self.rank * R:(self.rank + 1) * R]
-        g, ginv, y_used = self.G, None, Y_full
-        if self.solver == "transformed":
-            # G = L L^T; in the coordinates y~ = L^-1 y, x~ = L^T x the row systems are (I + (w-1) sum y~ y~^T) x~ =
-            # w sum y~, so the CG iteration carries no dense K x K product (three skinny GEMMs per half sweep instead)
-            _lib.check(L.cymf_chol_transforms_dev(_lib.ptr(self.g64), K, ld, add_diag, self.dtype, _lib.ptr(self.By),
-                                                  _lib.ptr(self.Bfwd), _lib.ptr(self.Bbwd), _lib.ptr(self.d_info), stream))
-            yt = self.Yt[:Y_full.shape[0]]
-            _lib.check(L.cymf_rows_times_matrix_dev(_lib.ptr(Y_full), _lib.ptr(yt), _lib.ptr(self.By), self.dtype,
-                                                    Y_full.shape[0], ld, stream))
-            _lib.check(L.cymf_rows_times_matrix_dev(_lib.ptr(x_blk), _lib.ptr(x_blk), _lib.ptr(self.Bfwd), self.dtype,
-                                                    R, ld, stream))                       # warm start in the new coordinates
-            g, y_used = None, yt
-        elif self.solver == "pcg":                               # G^-1 as CG preconditioner (f64 Gauss-Jordan, one CTA)
-            _lib.check(L.cymf_spd_inverse_dev(_lib.ptr(self.g64), K, ld, add_diag, self.dtype, _lib.ptr(self.Ginv), stream))
-            ginv = self.Ginv
-        # rows of the block are sorted heaviest first: 16 warps per row for the longest, then 8, then 4.  The three
-        # class kernels are independent (disjoint rows, own work queues): the two heavy classes go to side streams
-        # so that their tails -- a handful of very long rows -- drain underneath the bulk of the short rows.
+        yt = self.Yt[other]
+        es = 4 if self.dtype == _lib.F32 else 8
+        stream = _lib.stream_ptr()
+        # warm start in the coordinates x~ = L^T x of the fixed side's Cholesky factor
+        _lib.check(L.cymf_rows_times_matrix_dev(_lib.ptr(x_blk), _lib.ptr(x_blk), _lib.ptr(self.Bfwd), self.dtype, R, ld, stream))
         main = torch.cuda.current_stream()
-        if self._side is None:
-            self._side = [torch.cuda.Stream(device=self.dev) for _ in range(3)]
-        fork = torch.cuda.Event()
-        fork.record(main)
-        start, joins = 0, []
+        start, joins, fork = 0, [], None
         if heavy:
-            # the few very long rows: K x K matrix built once by many CTAs on the tensor cores, solved directly
+            # the few very long rows: K x K matrix built once by MANY CTAs on the tensor cores, solved directly
             nh, first_host, first_dev = heavy
-            st = self._side[2] if self.overlap_classes else main
+            st = self._side_streams[2] if self.overlap_classes else main
             if st is not main:
+                fork = torch.cuda.Event()
+                fork.record(main)
                 st.wait_event(fork)
             with torch.cuda.stream(st):
                 _lib.check(L.cymf_als_heavy_rows_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order), nh,
                                                      _lib.ptr(first_dev), int(first_host[-1]), _lib.ptr(x_blk),
-                                                     _lib.ptr(y_used), None, 0.0, self.dtype, K, ld, self.weight,
+                                                     _lib.ptr(yt), None, 0.0, self.dtype, K, ld, self.weight,
                                                      _lib.ptr(self.ws_heavy), self.ws_heavy.numel(), _lib.stream_ptr()))
                 if st is not main:
                     done = torch.cuda.Event()
@@ -425,62 +470,164 @@ class AlsSession(object):
                     joins.append(done)
             start = nh
         if self.row_solver == "tc":
-            count = sum(classes)
-            if count:
-                _lib.check(L.cymf_als_rows_tc_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order[start:]), count,
-                                                  _lib.ptr(x_blk), _lib.ptr(y_used), self.dtype, K, ld, self.weight,
-                                                  self.cg_tol, self.cg_max_iter, _lib.ptr(self.queue),
-                                                  _lib.ptr(self.d_stats), _lib.stream_ptr()))
-            classes = (0, 0, 0)
-        for c, (width, count) in enumerate(zip((16, 8, 4), classes)):
-            if count:
-                st = self._side[c] if (c < 2 and self.overlap_classes) else main
+            n_rows = start + sum(classes)
+            n_long = max(self._n_long[id(csr[0])], start)     # rows [start, n_long) one-pass, [n_long, n_rows) streamed
+            count = n_long - start
+            if n_rows > n_long:
+                st = self._side_streams[0] if self.overlap_classes else main
                 if st is not main:
+                    if fork is None:
+                        fork = torch.cuda.Event()
+                        fork.record(main)
                     st.wait_event(fork)
                 with torch.cuda.stream(st):
-                    _lib.check(L.cymf_als_cg_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order[start:]), count,
-                                                 _lib.ptr(x_blk), _lib.ptr(y_used), _lib.ptr(g), _lib.ptr(ginv),
-                                                 self.dtype, K, ld,
-                                                 self.weight, self.cg_tol, self.cg_max_iter, width, self.stage_rows,
-                                                 _lib.ptr(self.queue[c:]), _lib.ptr(self.d_stats), _lib.stream_ptr()))
+                    _lib.check(L.cymf_als_cg_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order[n_long:]),
+                                                 n_rows - n_long, _lib.ptr(x_blk), _lib.ptr(yt), None, None, self.dtype,
+                                                 K, ld, self.weight, self.cg_tol, self.cg_max_iter, 4, self.stage_rows,
+                                                 _lib.ptr(self.queue[1:]), _lib.ptr(self.d_stats), _lib.stream_ptr()))
                     if st is not main:
                         done = torch.cuda.Event()
                         done.record(st)
                         joins.append(done)
-            start += count
+            if count:
+                if self.kernel_events is not None:
+                    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    k0.record(main)
+                _lib.check(L.cymf_als_rows_tc_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order[start:]), count,
+                                                  _lib.ptr(x_blk), _lib.ptr(yt), self.dtype, K, ld, self.weight,
+                                                  self.cg_tol, self.cg_max_iter, _lib.ptr(self.queue),
+                                                  _lib.ptr(self.d_stats), stream))
+                if self.kernel_events is not None:
+                    k1.record(main)
+                    # bytes this launch must move: gathered item vectors + their indices, solved rows + their indptr
+                    self.kernel_events.append((int(csr[1].numel()) * (K * es + 4) + count * (K * es + 8), k0, k1))
+        else:
+            # streaming CG kernel (f64, or A/B runs): 16 warps per row for the longest rows, then 8, then 4; the
+            # classes are independent (disjoint rows, own work queues), the two heavy ones go to side streams
+            for c, (width, count) in enumerate(zip((16, 8, 4), classes)):
+                if count:
+                    st = self._side_streams[c] if (c < 2 and self.overlap_classes) else main
+                    if st is not main:
+                        if fork is None:
+                            fork = torch.cuda.Event()
+                            fork.record(main)
+                        st.wait_event(fork)
+                    with torch.cuda.stream(st):
+                        _lib.check(L.cymf_als_cg_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order[start:]), count,
+                                                     _lib.ptr(x_blk), _lib.ptr(yt), None, None, self.dtype, K, ld,
+                                                     self.weight, self.cg_tol, self.cg_max_iter, width, self.stage_rows,
+                                                     _lib.ptr(self.queue[c:]), _lib.ptr(self.d_stats), _lib.stream_ptr()))
+                        if st is not main:
+                            done = torch.cuda.Event()
+                            done.record(st)
+                            joins.append(done)
+                start += count
         for done in joins:
             main.wait_event(done)
+        # back to the original coordinates (this rank's block only; the other ranks receive x~ of the NEXT transform)
+        _lib.check(L.cymf_rows_times_matrix_dev(_lib.ptr(x_blk), _lib.ptr(x_blk), _lib.ptr(self.Bbwd), self.dtype, R, ld,
+                                                _lib.stream_ptr()))
+        self._stale[side] = self.dist is not None
+
+    def _half_transformed(self, side):
+        other = "item" if side == "user" else "user"
+        if self._pub_side != other:                           # first call, after restore(), or two half sweeps of the
+            self._publish(other)                              # same side in a row: (re)publish the fixed side
+        self._solve(side)
+        self._publish(side)
+        self._pub_side = side
+
+    def _half_legacy(self, X_full, R, csr, order, Y_full, Ry, classes):
+        """solver = "cg" / "pcg": CG on the untransformed systems (G p product inside every iteration); kept for A/B
+        comparisons.  Full replicas in the original coordinates, NCCL collectives."""
+        L, K, ld = self._L, self.K, self.ld
         stream = _lib.stream_ptr()
-        if self.solver == "transformed" and self.peer is not None:
-            # back-transform + all-gather in one kernel: every solved row is stored into all replicas over NVLink
-            hdl, ptrs = self.peer[X_full.data_ptr()]
-            off = self.rank * R * ld * es
-            outs = (C.c_void_p * self.world)(*[p + off for p in ptrs])
-            _lib.check(L.cymf_rows_times_matrix_multi_dev(_lib.ptr(x_blk), outs, self.world, _lib.ptr(self.Bbwd),
-                                                          self.dtype, R, ld, stream))
-            hdl.barrier(channel=0)                               # all blocks have landed in this rank's replica
-            return
-        if self.solver == "transformed":
-            _lib.check(L.cymf_rows_times_matrix_dev(_lib.ptr(x_blk), _lib.ptr(x_blk), _lib.ptr(self.Bbwd), self.dtype,
-                                                    R, ld, stream))                       # back to the original coordinates
+        if self.dist:
+            y_blk = Y_full[self.rank * Ry:(self.rank + 1) * Ry]
+            _lib.check(L.cymf_gram_dev(_lib.ptr(y_blk), self.dtype, Ry, K, ld, self.wd, 0, _lib.ptr(self.ws),
+                                       self.ws.numel(), _lib.ptr(self.g64), None, stream))
+            self.dist.all_reduce(self.g64)
+            _lib.check(L.cymf_gram_finalize_dev(_lib.ptr(self.g64), self.dtype, K, ld, self.wd, _lib.ptr(self.G), stream))
+            add_diag = self.wd
+        else:
+            _lib.check(L.cymf_gram_dev(_lib.ptr(Y_full), self.dtype, Y_full.shape[0], K, ld, self.wd, 1,
+                                       _lib.ptr(self.ws), self.ws.numel(), _lib.ptr(self.g64), _lib.ptr(self.G), stream))
+            add_diag = 0.0
+        x_blk = X_full[self.rank * R:(self.rank + 1) * R]
+        ginv = None
+        if self.solver == "pcg":                                 # G^-1 as CG preconditioner (f64 Gauss-Jordan, one CTA)
+            _lib.check(L.cymf_spd_inverse_dev(_lib.ptr(self.g64), K, ld, add_diag, self.dtype, _lib.ptr(self.Ginv), stream))
+            ginv = self.Ginv
+        start = 0
+        for c, (width, count) in enumerate(zip((16, 8, 4), classes)):
+            if count:
+                _lib.check(L.cymf_als_cg_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order[start:]), count,
+                                             _lib.ptr(x_blk), _lib.ptr(Y_full), _lib.ptr(self.G), _lib.ptr(ginv),
+                                             self.dtype, K, ld, self.weight, self.cg_tol, self.cg_max_iter, width,
+                                             self.stage_rows, _lib.ptr(self.queue[c:]), _lib.ptr(self.d_stats), stream))
+            start += count
         if self.dist:
             self.dist.all_gather_into_tensor(X_full, x_blk)
 
     def user_half(self):
-        self._half(self.dW, self.Ru, self.csr_u, self.order_u, self.dH, self.Ri, self.classes_u, self.heavy_u)
+        if self.solver == "transformed":
+            return self._half_transformed("user")
+        self._half_legacy(self.dW, self.Ru, self.csr_u, self.order_u, self.dH, self.Ri, self.classes_u)
 
     def item_half(self):
-        self._half(self.dH, self.Ri, self.csr_i, self.order_i, self.dW, self.Ru, self.classes_i, self.heavy_i)
+        if self.solver == "transformed":
+            return self._half_transformed("item")
+        self._half_legacy(self.dH, self.Ri, self.csr_i, self.order_i, self.dW, self.Ru, self.classes_i)
+
+    def _sync_replicas(self):
+        """Bring every rank's copy of dW / dH up to date (the half sweeps only exchange the transformed rows).  A
+        collective: download(), dense_f64(), residual() and snapshot() call it on all ranks."""
+        if self.dist:
+            for side, X_full, R in (("user", self.dW, self.Ru), ("item", self.dH, self.Ri)):
+                if self._stale[side]:
+                    self.dist.all_gather_into_tensor(X_full, X_full[self.rank * R:(self.rank + 1) * R].clone())
+                    self._stale[side] = False
 
     def epoch(self):
+        """One epoch = user half sweep + item half sweep (wmf.pyx:111-112).  From the second epoch on the whole
+        sequence (about twenty kernels, the cross-rank barriers included) is replayed as ONE CUDA graph."""
         import torch
         with torch.cuda.device(self.dev):
+            if (self.use_graph and self.solver == "transformed" and self._pub_side == "item"
+                    and self.kernel_events is None and self.graph_error is None):
+                if self._graph is None:
+                    self._capture()
+                if self._graph is not None:
+                    self._graph.replay()
+                    self._stale = {"user": self.dist is not None, "item": self.dist is not None}
+                    self.epochs_done += 1
+                    return
             self.user_half()
             self.item_half()
         self.epochs_done += 1
 
+    def _capture(self):
+        import torch
+        try:
+            torch.cuda.synchronize(self.dev)
+            if self.dist:
+                self.dist.barrier()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.user_half()
+                self.item_half()
+            self._graph = g
+        except Exception as exc:                                  # noqa: BLE001 - eager launches are always correct
+            import warnings
+            self.graph_error = repr(exc)
+            self._graph = None
+            warnings.warn(f"cymf_b200.WMF: CUDA graph capture of the epoch failed, launching eagerly: {self.graph_error}",
+                          RuntimeWarning)
+            torch.cuda.synchronize(self.dev)
+
     def download(self, W, H):
         import torch
+        self._sync_replicas()
         with torch.cuda.device(self.dev):
             for dev_m, row_slot, out in ((self.dW, self.d_row_slot_u, W), (self.dH, self.d_row_slot_i, H)):
                 _lib.download_factor(dev_m.index_select(0, row_slot), self.K, out)   # back to the caller's row order
@@ -489,6 +636,7 @@ class AlsSession(object):
         """(W, H) as dense float64 DEVICE tensors in the caller's row order -- what the on-device evaluator scores."""
         import torch
         out = []
+        self._sync_replicas()
         with torch.cuda.device(self.dev):
             for m, slots in ((self.dW, self.slot_u), (self.dH, self.slot_i)):
                 t = torch.empty((m.shape[0], self.K), dtype=torch.float64, device=self.dev)
@@ -502,12 +650,51 @@ class AlsSession(object):
                 out.append(t.index_select(0, self._unperm[key]))
         return tuple(out)
 
+    def residual(self, side, sample=24, seed=0):
+        """Parity property at sizes no CPU oracle reaches: the largest relative residual, evaluated in float64 from
+        the device-resident factors, of the reference's own per-row system (cymf/wmf.pyx:161-168)
+            (Y^T Y + wd I + (w - 1) sum_{c in row} y_c y_c^T) x = w sum_{c in row} y_c
+        over `sample` random non-empty rows of this rank's block plus its heaviest row; also asserts that rows without
+        entries are zero (wmf.pyx:154-156).  Call right after `user_half()` / `item_half()` (side = "user" / "item")."""
+        import torch
+        self._sync_replicas()
+        gen = torch.Generator(device=self.dev)
+        gen.manual_seed(int(seed))
+        X_full, R, csr, Y_full = ((self.dW, self.Ru, self.csr_u, self.dH) if side == "user" else
+                                  (self.dH, self.Ri, self.csr_i, self.dW))
+        K = self.K
+        with torch.cuda.device(self.dev):
+            Y = Y_full[:, :K].double()
+            G = Y.T @ Y + self.wd * torch.eye(K, dtype=torch.float64, device=self.dev)
+            ip, ix = csr
+            lens = ip[1:] - ip[:-1]
+            nonempty = torch.nonzero(lens > 0).flatten()
+            if nonempty.numel() == 0:
+                return 0.0
+            pick = nonempty[torch.randint(0, nonempty.numel(), (int(sample),), device=self.dev, generator=gen)]
+            pick = torch.cat([pick, torch.argmax(lens).reshape(1)])     # and the heaviest row of the block
+            worst = 0.0
+            for q in pick.tolist():
+                cols = ix[int(ip[q]):int(ip[q + 1])].long()
+                Yr = Y[cols]
+                A = G + (self.weight - 1.0) * (Yr.T @ Yr)
+                b = self.weight * Yr.sum(0)
+                x = X_full[self.rank * R + q, :K].double()
+                worst = max(worst, float(torch.linalg.norm(A @ x - b) / torch.linalg.norm(b)))
+            empty = torch.nonzero(lens == 0).flatten()
+            if empty.numel():                                           # wmf.pyx:154-156
+                assert not X_full[self.rank * R + empty[:64]].any()
+        return worst
+
     def snapshot(self):
+        self._sync_replicas()
         return self.dW.clone(), self.dH.clone()
 
     def restore(self, snap):
         self.dW.copy_(snap[0])
         self.dH.copy_(snap[1])
+        self._stale = {"user": False, "item": False}
+        self._pub_side = None                                 # the fixed side must be transformed again
 
     def stats(self):
         """(CG iterations summed over rows, rows that stopped at cg_max_iter).  Raises if a Gram matrix Y^T Y + wd I

@@ -254,6 +254,13 @@ int cymf_gram_dev(const void *Y, int dtype, int64_t n, int32_t K, int32_t ld, do
 int cymf_gram_finalize_dev(const double *in_f64, int dtype, int32_t K, int32_t ld, double weight_decay,
                            void *out_native, void *stream);
 
+/* Multi-GPU Gram all-reduce without NCCL: out_f64 [K,K] = sum over the n_parts (1..8) dense [K,K] f64 partials
+ * (host array of device pointers; peers' symmetric buffers over NVLink) in index order, + weight_decay on the diagonal
+ * (cymf/wmf.pyx:142-143 for a factor matrix whose rows are sharded over ranks).  The caller orders the ranks' writes
+ * before this kernel with a cross-rank barrier. */
+int cymf_gram_sum_dev(const double *const *parts, int32_t n_parts, int32_t K, double weight_decay, double *out_f64,
+                      void *stream);
+
 /* Solves the rows listed in `order` (n_solve row ids, heaviest first) of
  *     (G + (weight-1) sum_{i in row} y_i y_i^T) x = weight sum_{i in row} y_i            (wmf.pyx:158-168)
  * by conjugate gradient, warm-started from the current content of X, until |residual| <= cg_tol * |rhs| or

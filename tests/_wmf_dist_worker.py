@@ -82,7 +82,7 @@ def nccl_main():
     train, _ = cymf.synth.movielens_like("ml-1m")
     K = 64
     for dtype, tol in (("float64", 1e-9), ("float32", 2e-5)):
-        m = cymf.WMF(K, 0.01, 10.0, dtype=dtype)
+        m = cymf.WMF(K, 0.01, 10.0, dtype=dtype, distributed=True)
         m.fit(train, 2, 1, verbose=False)                      # sharded over all ranks
         s = cymf.WMF(K, 0.01, 10.0, dtype=dtype, distributed=False)
         s.fit(train, 2, 1, verbose=False)                      # every rank alone
@@ -94,10 +94,13 @@ def nccl_main():
         lo, hi = t.clone(), t.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         assert torch.equal(lo, hi), "ranks disagree on W"      # replicas are bit-identical across ranks
-        n = cymf.WMF(K, 0.01, 10.0, dtype=dtype, peer_gather=False)
+        n = cymf.WMF(K, 0.01, 10.0, dtype=dtype, peer_gather=False, distributed=True)
         n.fit(train, 2, 1, verbose=False)                      # same sharding, blocks exchanged by NCCL all-gather
         assert n.gather_mode_ == "nccl"
-        assert np.array_equal(n.W, m.W) and np.array_equal(n.H, m.H), "peer-store and NCCL gathers differ"
+        # same factors whichever transport carries the exchange (the Gram partials are summed in rank order by the
+        # peer-load kernel and in NCCL's order by all_reduce: last-bit differences in G only)
+        for a_, b_ in ((n.W, m.W), (n.H, m.H)):
+            assert np.abs(a_ - b_).max() <= (1e-11 if dtype == "float64" else 2e-6) * np.abs(b_).max(), "peer-store and NCCL paths differ"
     dist.destroy_process_group()
 
 

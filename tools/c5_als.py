@@ -26,33 +26,9 @@ from cymf_b200.synth import synth_implicit_device as synth_c5_device  # noqa: E4
 
 
 def residuals(sess, side, sample, seed):
-    """Checker for sizes no CPU oracle can reach: relative residual (f64, torch) of the reference's own per-row system
-    (cymf/wmf.pyx:161-168)  (Y^T Y + wd I + (w - 1) sum_{c in row} y_c y_c^T) x = w sum_{c in row} y_c  for `sample`
-    random rows of the block the session just solved plus its heaviest row; asserts that rows without entries are
-    zero (wmf.pyx:154-156).  Call right after `sess.user_half()` / `sess.item_half()`."""
-    torch.manual_seed(seed)
-    X_full, R, csr, Y_full = ((sess.dW, sess.Ru, sess.csr_u, sess.dH) if side == "user" else
-                              (sess.dH, sess.Ri, sess.csr_i, sess.dW))
-    K = sess.K
-    Y = Y_full[:, :K].double()
-    G = Y.T @ Y + sess.wd * torch.eye(K, dtype=torch.float64, device=Y.device)
-    ip, ix = csr
-    lens = ip[1:] - ip[:-1]
-    nonempty = torch.nonzero(lens > 0).flatten()
-    pick = nonempty[torch.randint(0, nonempty.numel(), (sample,), device=Y.device)]
-    pick = torch.cat([pick, torch.argmax(lens).reshape(1)])         # and the heaviest row of the block
-    worst = 0.0
-    for q in pick.tolist():
-        cols = ix[int(ip[q]):int(ip[q + 1])].long()
-        Yr = Y[cols]
-        A = G + (sess.weight - 1.0) * (Yr.T @ Yr)
-        b = sess.weight * Yr.sum(0)
-        x = X_full[sess.rank * R + q, :K].double()
-        worst = max(worst, float(torch.linalg.norm(A @ x - b) / torch.linalg.norm(b)))
-    empty = torch.nonzero(lens == 0).flatten()
-    if empty.numel():                                               # wmf.pyx:154-156: rows without entries are zero
-        assert not X_full[sess.rank * R + empty[:64]].any()
-    return worst
+    """Checker for sizes no CPU oracle can reach: `AlsSession.residual` (relative f64 residual of the reference's
+    per-row normal equations, cymf/wmf.pyx:161-168, on sampled rows + the heaviest row of the block)."""
+    return sess.residual(side, sample, seed)
 
 
 def main():
@@ -102,7 +78,8 @@ def main():
     launches0 = _lib.launch_count()
     t0 = time.perf_counter()
     sess = AlsSession((indptr, indices, (U, I)), W, H, 0.01, 10.0, K=K, dtype="float32", cg_tol=args.cg_tol, cg_max_iter=2 * K,
-                      stage_rows=args.stage_rows, overlap_classes=not args.no_overlap, heavy_min=args.heavy_min)
+                      stage_rows=args.stage_rows, overlap_classes=not args.no_overlap, heavy_min=args.heavy_min,
+                      distributed=world > 1)
     sync()
     t_prep = time.perf_counter() - t0
     prep_launches = _lib.launch_count() - launches0
