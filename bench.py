@@ -556,23 +556,30 @@ def time_als_main(train, K, steps, warmup, sync_all, world, hbm):
     sync_all()
     it0 = s.stats()[0]
     l0 = _lib.launch_count()
-    s.kernel_events = []
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     evs[0].record()
     for t in range(steps):
-        s.epoch()
+        s.epoch()                                            # from the second epoch on: one CUDA-graph replay per epoch
         evs[t + 1].record()
     sync_all()
     launches = _lib.launch_count() - l0
-    kev, s.kernel_events = s.kernel_events, None
+    iters = s.stats()[0] - it0
     per_step = [evs[t].elapsed_time(evs[t + 1]) * 1e-3 for t in range(steps)]
+    graphed = s._graph is not None
+    if graphed:                                              # replays do not pass through the C entry points:
+        launches = steps * s.graph_launches                  # kernels of this library captured in the graph, per replay
+    # the row-solver launches alone, eagerly launched with their own CUDA events on the launching stream
+    s.kernel_events = []
+    for _ in range(max(2, min(steps, 5))):
+        s.epoch()
+    sync_all()
+    kev, s.kernel_events = s.kernel_events, None
     k_bytes = float(sum(b for b, _, _ in kev))
     k_sec = float(sum(e0.elapsed_time(e1) for _, e0, e1 in kev)) * 1e-3
     t = torch.tensor([sum(per_step), k_sec], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     secs_all = float(t[0])
-    iters = s.stats()[0] - it0
     # parity scalar: one more epoch, each half sweep checked right after it ran (the other side is still the one it
     # was solved against)
     s.user_half()
@@ -590,7 +597,7 @@ def time_als_main(train, K, steps, warmup, sync_all, world, hbm):
            "kernel_launches": len(kev), "bytes_per_epoch": s.bytes_per_epoch,
            "cg_iterations_per_row": iters * world / (steps * rows), "unconverged_rows": s.stats()[1],
            "gather": "peer-store (fused into the GEMM epilogue)" if s.peer else ("nccl all-gather" if s.dist else "single"),
-           "row_solver": s.row_solver, "peer_error": s.peer_error,
+           "row_solver": s.row_solver, "peer_error": s.peer_error, "cuda_graph": graphed, "graph_error": s.graph_error,
            "parity": {"rel_residual": float(r.max()), "user_rows": float(r[0]), "item_rows": float(r[1]),
                       "rows_checked_per_side_per_rank": 25, "factors_finite": bool(fin.item() > 0),
                       "what": "max over ranks of |A x - b| / |b| in float64 for the reference's per-row system "
@@ -799,7 +806,7 @@ def main():
                              "note": "the fixed side (<= 71 MB) fits the 126 MB L2 at this shape, so algorithmic bytes/s "
                                      "may exceed DRAM bytes/s"},
                 "als": {k: main_res[k] for k in ("cg_iterations_per_row", "unconverged_rows", "gather", "row_solver",
-                                                 "peer_error")},
+                                                 "peer_error", "cuda_graph", "graph_error")},
                 "cpu_baseline": cpu, "extra": extra}
         print(json.dumps(line))
     if world > 1:

@@ -145,8 +145,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) als_rows_tc_kernel(const RowSo
         unsigned long long S2[HC / 2];                             // this thread's half of row m of S, packed pairs
 
         // this thread's 16 items of chunk c: element m of y~_i for i = 32 c + 16 h + j
-        float cur[16];
-        auto gather16 = [&](int c) {
+        auto gather16 = [&](float (&cur)[16], int c) {
             const int base = c * CHUNK_K + 16 * h;
             if (!m_on || base >= nnz) {
 #pragma unroll
@@ -204,10 +203,10 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) als_rows_tc_kernel(const RowSo
             fence_before_sync();
         };
 
-        gather16(0);
         float bs = 0.f;
         int fold = -1;                                            // chain that has ended and is not yet in S
-        for (int c = 0; c < nchunks; ++c, ++issued) {
+        // one chunk: wait for its stage, split + store this thread's 16 values, hand the stage to the issuer
+        auto process = [&](int c, float (&cur)[16], bool refill, bool may_fold) {
             // index blocks of long rows (three buffers): block b+1 is fetched while block b's first chunks are staged and
             // published by a CTA barrier two chunks before its first use (the gather of chunk 8b+8 is issued in
             // iteration 8b+7); warps drift apart by at most ROW_STAGES chunks in between
@@ -232,7 +231,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) als_rows_tc_kernel(const RowSo
                 *reinterpret_cast<float4 *>(t_lo + o) = sub4(v, hi4);
                 bs += (v.x + v.y) + (v.z + v.w);                  // wmf.pyx:163
             }
-            if (c + 1 < nchunks) gather16(c + 1);                 // in flight underneath the MMAs
+            if (refill && c + 1 < nchunks) gather16(cur, c + 1);  // in flight underneath the MMAs
             fence_async_smem();                                   // generic-proxy writes -> visible to the tensor core
             fence_before_sync();
             __syncwarp();
@@ -266,8 +265,22 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) als_rows_tc_kernel(const RowSo
             ph_full ^= sbit;
             pend |= sbit;
             stage = stage + 1 == ROW_STAGES ? 0 : stage + 1;
-            if (fold >= 0) { fold_chain(fold); fold = -1; }       // previous chain, while this one's MMAs run
+            ++issued;
+            if (may_fold && fold >= 0) { fold_chain(fold); fold = -1; }       // previous chain, while this one's MMAs run
             if (chain_last) { fold = acc; acc ^= 1; }
+        };
+        {
+            // the first two chunks (all of a row of <= 64 entries): both gathers are issued before the first value is
+            // needed, one memory round trip for the two
+            float c0[16], c1[16];
+            gather16(c0, 0);
+            if (nchunks > 1) gather16(c1, 1);
+            process(0, c0, false, false);                         // (no chain can end before chunk ROW_CHAIN - 1)
+            if (nchunks > 1) {
+                if (nchunks > 2) gather16(c0, 2);
+                process(1, c1, false, false);
+                for (int c = 2; c < nchunks; ++c) process(c, c0, true, true);      // steady state: one chunk ahead
+            }
         }
         if (tid == 0) {
             rowq[(row_i + 1) % 3] = RowInfo{rB, (int)(hiB - loB), loB};        // row i+1: visible after the next barrier
@@ -282,14 +295,20 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) als_rows_tc_kernel(const RowSo
         // barrier per iteration.
         auto matvec = [&](const float *vec) -> float {           // this thread's half of row m of S times vec
             unsigned long long a0 = 0ull, a1 = 0ull, a2 = 0ull, a3 = 0ull;
-            const ulonglong2 *pv = reinterpret_cast<const ulonglong2 *>(vec + h * HC);
+            const uint32_t pv = smem_u32(vec + h * HC);
+            constexpr int NL = HC / 4;                            // 16-byte pieces of this thread's half of vec
+            ulonglong2 u[4];                                      // four loads in flight: one shared-memory latency per four
+            auto lds = [&](ulonglong2 &d, int t) {                // volatile: issue order is the program order
+                asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(d.x), "=l"(d.y) : "r"(pv + 16u * (uint32_t)t) : "memory");
+            };
 #pragma unroll
-            for (int t = 0; t < HC / 4; t += 2) {
-                const ulonglong2 u = pv[t], v = pv[t + 1];
-                fma2(a0, S2[2 * t], u.x);
-                fma2(a1, S2[2 * t + 1], u.y);
-                fma2(a2, S2[2 * t + 2], v.x);
-                fma2(a3, S2[2 * t + 3], v.y);
+            for (int t = 0; t < 4 && t < NL; ++t) lds(u[t], t);
+#pragma unroll
+            for (int t = 0; t < NL; ++t) {
+                const ulonglong2 w = u[t & 3];
+                if (t + 4 < NL) lds(u[t & 3], t + 4);
+                if (t & 1) { fma2(a2, S2[2 * t], w.x); fma2(a3, S2[2 * t + 1], w.y); }
+                else { fma2(a0, S2[2 * t], w.x); fma2(a1, S2[2 * t + 1], w.y); }
             }
             float s0, s1, s2, s3, s4, s5, s6, s7;
             unpack2(a0, s0, s1); unpack2(a1, s2, s3); unpack2(a2, s4, s5); unpack2(a3, s6, s7);

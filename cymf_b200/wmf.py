@@ -155,6 +155,13 @@ def _relabel(Xcsr, row_slots, col_new_index, n_cols):
                              shape=(rows.shape[0], n_cols))
 
 
+# Symmetric (NVLink peer-mapped) buffers are expensive to set up (an allocation + a rendezvous of all ranks, ~0.1 s
+# each), and `WMF.fit` builds one session per call: buffers are kept per (name, shape, dtype, device, world) and reused
+# by later sessions of the same process group.  Every element is rewritten before it is read (publish step), so no
+# stale content can leak between fits.
+_SYMM_CACHE = {}
+
+
 class AlsSession(object):
     """Device-resident state of one `_fit_als` call (both CSR orientations of this rank's row blocks, full
     replicas of W and H in dealt order); `epoch()` = user half sweep + item half sweep (wmf.pyx:111-112)."""
@@ -168,7 +175,8 @@ class AlsSession(object):
         # rows of at most this many entries go to the streaming CG kernel even when the tensor-core solver is on: its
         # cost grows with the row length (~145 SM-clocks per entry) while the one-pass solver pays ~10 k SM-clocks per
         # row whatever its length (K x K CG from registers), so very short rows are cheaper streamed.  0 = never.
-        self.short_max = int(os.environ.get("CYMF_ALS_SHORT", "0"))
+        # Measured, ml-20m shape K=128 (gpurun_out r2_sweep_v5): 13.1 ms/epoch at 0, 12.15 at 96 and 128, 12.4 at 192.
+        self.short_max = int(os.environ.get("CYMF_ALS_SHORT", "112"))
         self.peer_error = None
         self._unperm = {}
         self.force_width = int(force_width)
@@ -241,7 +249,7 @@ class AlsSession(object):
             self._stale = {"user": False, "item": False}      # other ranks' blocks of dW / dH are out of date
             self._pub_side = None                             # side whose Yt / transforms were published last
             self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
-            self._graph, self.graph_error = None, None
+            self._graph, self.graph_error, self.graph_launches = None, None, 0
             self.use_graph = os.environ.get("CYMF_ALS_GRAPH", "1") == "1"
         self.epochs_done = 0
         self.kernel_events = None        # set to [] to record (algorithmic bytes, start, end) CUDA events per row-solver launch
@@ -314,12 +322,16 @@ class AlsSession(object):
             group = self.dist.group.WORLD
             gname = group.group_name if hasattr(group, "group_name") else group
             for name, old in (("user", self.Yt["user"]), ("item", self.Yt["item"]), ("gram", self.gpart)):
-                new = symm.empty(tuple(old.shape), dtype=old.dtype, device=self.dev)
+                key = (name, tuple(old.shape), old.dtype, str(self.dev), self.world, str(gname))
+                if key not in _SYMM_CACHE:
+                    new = symm.empty(tuple(old.shape), dtype=old.dtype, device=self.dev)
+                    hdl = symm.rendezvous(new, gname)
+                    ptrs = [int(p) for p in hdl.buffer_ptrs]
+                    if len(ptrs) != self.world or ptrs[self.rank] != new.data_ptr():
+                        raise RuntimeError("unexpected symmetric-memory layout")
+                    _SYMM_CACHE[key] = (new, hdl, ptrs)
+                new, hdl, ptrs = _SYMM_CACHE[key]
                 new.copy_(old)
-                hdl = symm.rendezvous(new, gname)
-                ptrs = [int(p) for p in hdl.buffer_ptrs]
-                if len(ptrs) != self.world or ptrs[self.rank] != new.data_ptr():
-                    raise RuntimeError("unexpected symmetric-memory layout")
                 moved.append((name, new, hdl, ptrs))
             ok = torch.ones(1, device=self.dev)
         except Exception as exc:                                   # noqa: BLE001 - any failure -> NCCL path
@@ -613,9 +625,11 @@ class AlsSession(object):
             if self.dist:
                 self.dist.barrier()
             g = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
             with torch.cuda.graph(g):
                 self.user_half()
                 self.item_half()
+            self.graph_launches = _lib.launch_count() - l0      # kernels of libcymf_b200 per replay
             self._graph = g
         except Exception as exc:                                  # noqa: BLE001 - eager launches are always correct
             import warnings
