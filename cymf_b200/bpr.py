@@ -82,7 +82,7 @@ class BPR(object):
             X = sparse.csr_matrix(X)
         else:
             raise ValueError()
-        X = X.astype(np.float64)
+        X = X.astype(np.float64, copy=False)     # the reference copies (wmf.pyx:84 / bpr.pyx:87); X is only read here
 
         self.valid_evaluator = valid_evaluator
         self.valid_dcg = -np.inf

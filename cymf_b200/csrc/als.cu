@@ -92,6 +92,59 @@ __global__ void __launch_bounds__(256) gram_partial_kernel(const T *__restrict__
         }
 }
 
+// K > 128 (the reference has no limit on num_components, cymf/wmf.pyx:44): one CTA per (slab, 64 x 64 output block).
+template <typename T>
+__global__ void __launch_bounds__(256) gram_wide_kernel(const T *__restrict__ Y, int64_t n, int K, int ld,
+                                                        double *__restrict__ partial) {
+    __shared__ T ta[GRAM_ROWS][65], tb[GRAM_ROWS][65];
+    const int nb = (K + 63) / 64, bi = blockIdx.y / nb, bj = blockIdx.y % nb;
+    const int tj = threadIdx.x & 15, ti = threadIdx.x >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    const int64_t r0 = (int64_t)blockIdx.x * GRAM_SLAB;
+    const int64_t r1 = r0 + GRAM_SLAB < n ? r0 + GRAM_SLAB : n;
+    for (int64_t base = r0; base < r1; base += GRAM_ROWS) {
+        for (int t = threadIdx.x; t < GRAM_ROWS * 64; t += 256) {
+            const int rr = t >> 6, c = t & 63;
+            const bool ok = base + rr < r1;
+            ta[rr][c] = ok && bi * 64 + c < K ? Y[(size_t)(base + rr) * ld + bi * 64 + c] : T(0);
+            tb[rr][c] = ok && bj * 64 + c < K ? Y[(size_t)(base + rr) * ld + bj * 64 + c] : T(0);
+        }
+        __syncthreads();
+        T part[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) part[a][b] = T(0);
+#pragma unroll 4
+        for (int rr = 0; rr < GRAM_ROWS; ++rr) {
+            T ya[4], yb[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { ya[a] = ta[rr][ti + 16 * a]; yb[a] = tb[rr][tj + 16 * a]; }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) part[a][b] += ya[a] * yb[b];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] += (double)part[a][b];      // 32-row products in T, summed in f64
+        __syncthreads();
+    }
+    double *out = partial + (size_t)blockIdx.x * K * K;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = bi * 64 + ti + 16 * a, j = bj * 64 + tj + 16 * b;
+            if (i < K && j < K) out[(size_t)i * K + j] = acc[a][b];
+        }
+}
+
 // Sum the slab partials in slab order (deterministic), optionally add wd on the diagonal.  out64: dense [K, K] f64;
 // outT: [ld, ld] of T with zero padding (the layout the CG kernel reads).
 template <typename T>
@@ -132,36 +185,54 @@ template <typename T> struct AlsArgs {
 
 // VW contiguous elements, naturally aligned (VW * sizeof(T) up to 32 bytes)
 template <int VW> __device__ __forceinline__ void ld_vec(const float *p, float (&v)[VW]) {
-    if constexpr (VW == 4) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    if constexpr (VW == 8) {
+        const float4 s = *reinterpret_cast<const float4 *>(p), t = *reinterpret_cast<const float4 *>(p + 4);
+        v[0] = s.x; v[1] = s.y; v[2] = s.z; v[3] = s.w; v[4] = t.x; v[5] = t.y; v[6] = t.z; v[7] = t.w;
+    } else if constexpr (VW == 4) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
     else if constexpr (VW == 2) { const float2 t = *reinterpret_cast<const float2 *>(p); v[0] = t.x; v[1] = t.y; }
     else v[0] = *p;
 }
 template <int VW> __device__ __forceinline__ void ld_vec(const double *p, double (&v)[VW]) {
-    if constexpr (VW == 4) {
+    if constexpr (VW == 8) {
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) { const double2 t = *reinterpret_cast<const double2 *>(p + e); v[e] = t.x; v[e + 1] = t.y; }
+    } else if constexpr (VW == 4) {
         const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
         v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
     } else if constexpr (VW == 2) { const double2 t = *reinterpret_cast<const double2 *>(p); v[0] = t.x; v[1] = t.y; }
     else v[0] = *p;
 }
 template <int VW> __device__ __forceinline__ void ldg_vec(const float *p, float (&v)[VW]) {
-    if constexpr (VW == 4) { const float4 t = __ldg(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    if constexpr (VW == 8) {
+        const float4 s = __ldg(reinterpret_cast<const float4 *>(p)), t = __ldg(reinterpret_cast<const float4 *>(p + 4));
+        v[0] = s.x; v[1] = s.y; v[2] = s.z; v[3] = s.w; v[4] = t.x; v[5] = t.y; v[6] = t.z; v[7] = t.w;
+    } else if constexpr (VW == 4) { const float4 t = __ldg(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
     else if constexpr (VW == 2) { const float2 t = __ldg(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y; }
     else v[0] = __ldg(p);
 }
 template <int VW> __device__ __forceinline__ void ldg_vec(const double *p, double (&v)[VW]) {
-    if constexpr (VW == 4) {
+    if constexpr (VW == 8) {
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) { const double2 t = __ldg(reinterpret_cast<const double2 *>(p + e)); v[e] = t.x; v[e + 1] = t.y; }
+    } else if constexpr (VW == 4) {
         const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p + 2));
         v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
     } else if constexpr (VW == 2) { const double2 t = __ldg(reinterpret_cast<const double2 *>(p)); v[0] = t.x; v[1] = t.y; }
     else v[0] = __ldg(p);
 }
 template <int VW> __device__ __forceinline__ void st_vec(float *p, const float (&v)[VW]) {
-    if constexpr (VW == 4) *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    if constexpr (VW == 8) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else if constexpr (VW == 4) *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
     else if constexpr (VW == 2) *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
     else *p = v[0];
 }
 template <int VW> __device__ __forceinline__ void st_vec(double *p, const double (&v)[VW]) {
-    if constexpr (VW == 4) {
+    if constexpr (VW == 8) {
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) *reinterpret_cast<double2 *>(p + e) = make_double2(v[e], v[e + 1]);
+    } else if constexpr (VW == 4) {
         *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
         *reinterpret_cast<double2 *>(p + 2) = make_double2(v[2], v[3]);
     } else if constexpr (VW == 2) *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
@@ -189,7 +260,7 @@ __device__ __forceinline__ void warp_allsum4(T &d0, T &d1, T &d2, T &d3, int lan
     d1 = __shfl_sync(0xffffffffu, k, 16);
     d3 = __shfl_sync(0xffffffffu, k, 24);
 }
-constexpr int CG_VEC = 128;           // capacity of the shared K-vectors (ld <= 128)
+constexpr int CG_VEC = 256;           // capacity of the shared K-vectors (ld <= 256: 8 elements per lane)
 
 // element offset of row r of an [n, ld] matrix; r >= 0, so the product is one unsigned wide multiply (IMAD.WIDE.U32)
 // instead of the sign-extending 64-bit multiply chain (6 -> 3 instructions per gathered row in the CG loops)
@@ -250,7 +321,8 @@ __device__ __forceinline__ void axpy4(T (&acc)[VW], T d0, const T (&y0)[VW], T d
     }
 }
 
-// NW warps cooperate on one row.  VW = elements of a K-vector per lane (1: ld<=32, 2: ld<=64, 4: ld<=128).
+// NW warps cooperate on one row.  VW = elements of a K-vector per lane (1: ld<=32, 2: ld<=64, 4: ld<=128, 8: ld<=256,
+// CTAs of at least 8 warps there: thread k owns element k of x, r, p).
 template <typename T, int VW, int NW>
 __global__ void __launch_bounds__(32 * NW) als_cg_kernel(const AlsArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -644,7 +716,11 @@ template <typename T> static int gram_impl(const T *Y, int64_t n, int K, int ld,
     if (slabs > 0) {
         if (K <= 32) gram_partial_kernel<T, 2><<<slabs, 256, 0, st>>>(Y, n, K, ld, partial);
         else if (K <= 64) gram_partial_kernel<T, 4><<<slabs, 256, 0, st>>>(Y, n, K, ld, partial);
-        else gram_partial_kernel<T, 8><<<slabs, 256, 0, st>>>(Y, n, K, ld, partial);
+        else if (K <= 128) gram_partial_kernel<T, 8><<<slabs, 256, 0, st>>>(Y, n, K, ld, partial);
+        else {
+            const int nb = (K + 63) / 64;
+            gram_wide_kernel<T><<<dim3((unsigned)slabs, (unsigned)(nb * nb)), 256, 0, st>>>(Y, n, K, ld, partial);
+        }
         CYMF_LAUNCHED();
     }
     gram_finish_kernel<T><<<(ld * ld + 255) / 256, 256, 0, st>>>(partial, slabs, K, ld, add_wd ? wd : 0.0, out64, outT);
@@ -683,13 +759,16 @@ template <typename T, int VW, int NW> static int launch_cg(AlsArgs<T> a, int32_t
 template <typename T, int NW> static int cg_by_width(const AlsArgs<T> &a, int32_t stage_rows, cudaStream_t st) {
     if (a.ld <= 32) return launch_cg<T, 1, NW>(a, stage_rows, st);
     if (a.ld <= 64) return launch_cg<T, 2, NW>(a, stage_rows, st);
-    return launch_cg<T, 4, NW>(a, stage_rows, st);
+    if (a.ld <= 128) return launch_cg<T, 4, NW>(a, stage_rows, st);
+    if constexpr (NW >= 8) return launch_cg<T, 8, NW>(a, stage_rows, st);
+    set_error("als: ld > 128 needs at least 8 warps per row");
+    return CYMF_EINVAL;
 }
 
 template <typename T> static int cg_impl(const AlsArgs<T> &a, int32_t warps_per_row, int32_t stage_rows, cudaStream_t st) {
     CYMF_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(int32_t), st));
     if (warps_per_row >= 16) return cg_by_width<T, 16>(a, stage_rows, st);
-    if (warps_per_row >= 8) return cg_by_width<T, 8>(a, stage_rows, st);
+    if (warps_per_row >= 8 || a.ld > 128) return cg_by_width<T, 8>(a, stage_rows, st);
     return cg_by_width<T, 4>(a, stage_rows, st);
 }
 
@@ -706,8 +785,8 @@ extern "C" int cymf_gram_dev(const void *Y, int dtype, int64_t n, int32_t K, int
                              int add_weight_decay, double *workspace, int64_t workspace_doubles,
                              double *out_f64, void *out_native, void *stream) {
     CYMF_REQUIRE(Y && workspace && (out_f64 || out_native), "null pointer");
-    CYMF_REQUIRE(n >= 0 && K > 0 && K <= 128 && ld >= K && ld % 4 == 0 && ld <= 128,
-                 "bad shape (WMF supports num_components <= 128, ld a multiple of 4)");
+    CYMF_REQUIRE(n >= 0 && K > 0 && K <= 256 && ld >= K && ld % 4 == 0 && ld <= 256,
+                 "bad shape (WMF supports num_components <= 256, ld a multiple of 4)");
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == CYMF_F32)
         return gram_impl<float>((const float *)Y, n, K, ld, weight_decay, add_weight_decay, workspace, workspace_doubles,
@@ -723,7 +802,7 @@ extern "C" int cymf_gram_dev(const void *Y, int dtype, int64_t n, int32_t K, int
 // all-reduced in f64
 extern "C" int cymf_gram_finalize_dev(const double *in_f64, int dtype, int32_t K, int32_t ld, double weight_decay,
                                       void *out_native, void *stream) {
-    CYMF_REQUIRE(in_f64 && out_native && K > 0 && K <= 128 && ld >= K && ld <= 128, "bad argument");
+    CYMF_REQUIRE(in_f64 && out_native && K > 0 && K <= 256 && ld >= K && ld <= 256, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == CYMF_F32)
         gram_finish_kernel<float><<<(ld * ld + 255) / 256, 256, 0, st>>>(in_f64, 1, K, ld, weight_decay, nullptr,
@@ -750,7 +829,7 @@ __global__ void gram_sum_kernel(const GramParts parts, int KK, int K, double wd,
 
 extern "C" int cymf_gram_sum_dev(const double *const *parts, int32_t n_parts, int32_t K, double weight_decay,
                                  double *out_f64, void *stream) {
-    CYMF_REQUIRE(parts && out_f64 && n_parts >= 1 && n_parts <= 8 && K > 0 && K <= 128, "bad argument");
+    CYMF_REQUIRE(parts && out_f64 && n_parts >= 1 && n_parts <= 8 && K > 0 && K <= 256, "bad argument");
     GramParts gp{};
     gp.n = n_parts;
     for (int r = 0; r < n_parts; ++r) { CYMF_REQUIRE(parts[r] != nullptr, "null partial"); gp.p[r] = parts[r]; }
@@ -1002,8 +1081,8 @@ extern "C" int cymf_als_cg_dev(const int64_t *indptr, const int32_t *indices, co
                                int32_t stage_rows, int32_t *queue, unsigned long long *stats, void *stream) {
     CYMF_REQUIRE(indptr && indices && order && X && Y && queue, "null pointer");
     CYMF_REQUIRE(G || !Ginv, "Ginv without G");
-    CYMF_REQUIRE(K > 0 && K <= 128 && ld >= K && ld % 4 == 0 && ld <= 128,
-                 "bad shape (WMF supports num_components <= 128, ld a multiple of 4)");
+    CYMF_REQUIRE(K > 0 && K <= 256 && ld >= K && ld % 4 == 0 && ld <= 256,
+                 "bad shape (WMF supports num_components <= 256, ld a multiple of 4)");
     CYMF_REQUIRE(cg_tol > 0 && cg_max_iter > 0, "bad CG parameters");
     if (n_solve <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1075,7 +1154,7 @@ extern "C" int cymf_als_half_host(const int32_t *indptr, const int32_t *indices,
                                   int64_t rows, int64_t n, int32_t K, double weight_decay, double weight,
                                   int dtype, double cg_tol, int32_t cg_max_iter, int64_t *cg_iterations_out) {
     CYMF_REQUIRE(indptr && indices && X && Y, "null pointer");
-    CYMF_REQUIRE(rows > 0 && n > 0 && K > 0 && K <= 128, "bad shape (WMF supports num_components <= 128)");
+    CYMF_REQUIRE(rows > 0 && n > 0 && K > 0 && K <= 256, "bad shape (WMF supports num_components <= 256)");
     CYMF_REQUIRE(dtype == CYMF_F32 || dtype == CYMF_F64, "unknown dtype");
     int ndev = 0;
     CYMF_CUDA(cudaGetDeviceCount(&ndev));
@@ -1083,7 +1162,8 @@ extern "C" int cymf_als_half_host(const int32_t *indptr, const int32_t *indices,
     if (cg_tol <= 0) cg_tol = dtype == CYMF_F32 ? 1e-6 : 1e-10;
     if (cg_max_iter <= 0) cg_max_iter = 2 * K;
     const size_t es = dtype == CYMF_F32 ? 4 : 8;
-    const bool tc_rows = dtype == CYMF_F32 && tc_enabled();            // one-pass tensor-core row solver (als_tc.cu)
+    const bool wide = K > 128;                                         // plain CG on the untransformed systems
+    const bool tc_rows = dtype == CYMF_F32 && tc_enabled() && !wide;   // one-pass tensor-core row solver (als_tc.cu)
     const int32_t ld = tc_rows ? (K + 31) / 32 * 32 : (K + 3) / 4 * 4;
     const int64_t nnz = indptr[rows];
     std::vector<int64_t> ip64((size_t)rows + 1);
@@ -1122,29 +1202,36 @@ extern "C" int cymf_als_half_host(const int32_t *indptr, const int32_t *indices,
     CYMF_CUDA(cudaMemcpyAsync(d_order, order.data(), (size_t)rows * 4, cudaMemcpyHostToDevice, st));
     CYMF_CUDA(cudaMemsetAsync(d_stats, 0, 16, st));
     CYMF_TRY(cymf_gram_dev(dY, dtype, n, K, ld, weight_decay, 1, ws, wsn, g64, dG, st));
-    // change of variables y~ = L^-1 y, x~ = L^T x (G = L L^T): the CG iteration then has no dense K x K product
-    void *dBy, *dBf, *dBb, *dYt;
-    CYMF_TRY(mem.get((char **)&dBy, (size_t)ld * ld * es));
-    CYMF_TRY(mem.get((char **)&dBf, (size_t)ld * ld * es));
-    CYMF_TRY(mem.get((char **)&dBb, (size_t)ld * ld * es));
-    CYMF_TRY(mem.get((char **)&dYt, (size_t)n * ld * es));
-    CYMF_TRY(cymf_chol_transforms_dev(g64, K, ld, 0.0, dtype, dBy, dBf, dBb, nullptr, st));
-    CYMF_TRY(cymf_rows_times_matrix_dev(dY, dYt, dBy, dtype, n, ld, st));
-    CYMF_TRY(cymf_rows_times_matrix_dev(dX, dX, dBf, dtype, rows, ld, st));
-    if (tc_rows) {
-        CYMF_TRY(cymf_als_rows_tc_dev(d_ip, d_ix, d_order, (int32_t)rows, dX, dYt, dtype, K, ld, weight, cg_tol,
-                                      cg_max_iter, d_queue, d_stats, st));
-        CYMF_TRY(cymf_rows_times_matrix_dev(dX, dX, dBb, dtype, rows, ld, st));
-    } else {   // heaviest rows with 16 warps per row, medium with 8, the rest with 4
-        std::vector<int64_t> len((size_t)rows);
-        for (int64_t t = 0; t < rows; ++t) len[(size_t)t] = indptr[order[(size_t)t] + 1] - indptr[order[(size_t)t]];
-        int64_t n16 = 0, n8 = 0;
-        CYMF_TRY(cymf_als_row_classes(len.data(), rows, dtype, ld, &n16, &n8));
-        const int64_t start[3] = {0, n16, n16 + n8}, count[3] = {n16, n8, rows - n16 - n8};
-        const int32_t width[3] = {16, 8, 4};
+    // heaviest rows with 16 warps per row, medium with 8, the rest with 4
+    std::vector<int64_t> len((size_t)rows);
+    for (int64_t t = 0; t < rows; ++t) len[(size_t)t] = indptr[order[(size_t)t] + 1] - indptr[order[(size_t)t]];
+    int64_t n16 = 0, n8 = 0;
+    CYMF_TRY(cymf_als_row_classes(len.data(), rows, dtype, ld, &n16, &n8));
+    const int64_t start[3] = {0, n16, n16 + n8}, count[3] = {n16, n8, rows - n16 - n8};
+    const int32_t width[3] = {16, 8, 4};
+    if (wide) {
+        // num_components > 128: CG on (G + (w-1) sum y y^T) x = w sum y itself, G p product inside every iteration
         for (int c = 0; c < 3; ++c)
-            CYMF_TRY(cymf_als_cg_dev(d_ip, d_ix, d_order + start[c], (int32_t)count[c], dX, dYt, nullptr, nullptr, dtype, K,
-                                     ld, weight, cg_tol, cg_max_iter, width[c], 0, d_queue, d_stats, st));
+            CYMF_TRY(cymf_als_cg_dev(d_ip, d_ix, d_order + start[c], (int32_t)count[c], dX, dY, dG, nullptr, dtype, K, ld,
+                                     weight, cg_tol, cg_max_iter, width[c], 0, d_queue, d_stats, st));
+    } else {
+        // change of variables y~ = L^-1 y, x~ = L^T x (G = L L^T): the CG iteration then has no dense K x K product
+        void *dBy, *dBf, *dBb, *dYt;
+        CYMF_TRY(mem.get((char **)&dBy, (size_t)ld * ld * es));
+        CYMF_TRY(mem.get((char **)&dBf, (size_t)ld * ld * es));
+        CYMF_TRY(mem.get((char **)&dBb, (size_t)ld * ld * es));
+        CYMF_TRY(mem.get((char **)&dYt, (size_t)n * ld * es));
+        CYMF_TRY(cymf_chol_transforms_dev(g64, K, ld, 0.0, dtype, dBy, dBf, dBb, nullptr, st));
+        CYMF_TRY(cymf_rows_times_matrix_dev(dY, dYt, dBy, dtype, n, ld, st));
+        CYMF_TRY(cymf_rows_times_matrix_dev(dX, dX, dBf, dtype, rows, ld, st));
+        if (tc_rows) {
+            CYMF_TRY(cymf_als_rows_tc_dev(d_ip, d_ix, d_order, (int32_t)rows, dX, dYt, dtype, K, ld, weight, cg_tol,
+                                          cg_max_iter, d_queue, d_stats, st));
+        } else {
+            for (int c = 0; c < 3; ++c)
+                CYMF_TRY(cymf_als_cg_dev(d_ip, d_ix, d_order + start[c], (int32_t)count[c], dX, dYt, nullptr, nullptr, dtype,
+                                         K, ld, weight, cg_tol, cg_max_iter, width[c], 0, d_queue, d_stats, st));
+        }
         CYMF_TRY(cymf_rows_times_matrix_dev(dX, dX, dBb, dtype, rows, ld, st));
     }
     CYMF_TRY(cymf_unpack_rows_dev(dX, stage, dtype, rows, K, ld, st));

@@ -21,6 +21,8 @@
 //     on (I + (w-1) S) x~ = b runs entirely out of registers -- one 64-FMA matvec per thread and three barriers
 //     per iteration -- warm-started from the current x~ and stopped at |r| <= tol |b| like the streaming kernel.
 // The row is read once: N (K s + 4) bytes per half sweep, the algorithmic figure of SURVEY.md 8(d).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace cymf {
@@ -403,6 +405,8 @@ template <int LD> static int launch_rows(const RowSolveArgs &a, cudaStream_t st)
 int tc_als_rows(const int64_t *indptr, const int32_t *indices, const int32_t *order, int32_t n_solve, float *X,
                 const float *Y, int ld, float weight, float tol2, int32_t max_iter, int32_t *queue,
                 unsigned long long *stats, cudaStream_t st) {
+    if (const char *v = getenv("CYMF_ALS_TC6"))              // A/B hook: the asynchronous-gather form of the kernel (als_tc6.cu)
+        if (v[0] == '1') return tc_als_rows6(indptr, indices, order, n_solve, X, Y, ld, weight, tol2, max_iter, queue, stats, st);
     CYMF_CUDA(cudaMemsetAsync(queue, 0, sizeof(int32_t), st));
     tc::RowSolveArgs a{indptr, indices, order, n_solve, X, Y, max_iter, weight, tol2, queue, stats};
     switch (ld) {

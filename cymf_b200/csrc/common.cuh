@@ -45,6 +45,9 @@ int tc_gram_gather(const float *Y, const int64_t *indptr, const int32_t *indices
 int tc_als_rows(const int64_t *indptr, const int32_t *indices, const int32_t *order, int32_t n_solve, float *X,
                 const float *Y, int ld, float weight, float tol2, int32_t max_iter, int32_t *queue,
                 unsigned long long *stats, cudaStream_t st);      // als_tc.cu
+int tc_als_rows6(const int64_t *indptr, const int32_t *indices, const int32_t *order, int32_t n_solve, float *X,
+                 const float *Y, int ld, float weight, float tol2, int32_t max_iter, int32_t *queue,
+                 unsigned long long *stats, cudaStream_t st);     // als_tc6.cu
 bool tc_enabled();      // false when the environment sets CYMF_NO_TCGEN05=1 (A/B comparisons in tests and tools)
 
 #define CYMF_TRY(expr)             \

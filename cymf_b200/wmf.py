@@ -47,8 +47,8 @@ class WMF(object):
         self.H = None
         if dtype not in _lib.DTYPES:
             raise ValueError("dtype must be 'float32' or 'float64'")
-        if self.num_components > 128:
-            raise ValueError("cymf_b200.WMF supports num_components <= 128")
+        if self.num_components > 256:
+            raise ValueError("cymf_b200.WMF supports num_components <= 256")
         self.dtype = dtype
         self.cg_tol = cg_tol
         self.cg_max_iter = cg_max_iter
@@ -81,7 +81,7 @@ class WMF(object):
             X = sparse.csr_matrix(X)
         else:
             raise ValueError()
-        X = X.astype(np.float64)
+        X = X.astype(np.float64, copy=False)     # the reference copies (wmf.pyx:84 / bpr.pyx:87); X is only read here
 
         self.valid_evaluator = valid_evaluator
         self.valid_dcg = -np.inf
@@ -182,6 +182,8 @@ class AlsSession(object):
         self.force_width = int(force_width)
         if solver not in ("transformed", "pcg", "cg"):
             raise ValueError("solver must be 'transformed', 'pcg' or 'cg'")
+        if int(K if K is not None else W.shape[1]) > 128:
+            solver = "cg"      # the Cholesky change of variables and the tensor-core kernels stop at K = 128: plain CG
         self.solver = solver
         import torch.distributed as dist
         self._L = _lib.lib()

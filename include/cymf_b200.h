@@ -241,6 +241,11 @@ int cymf_cooc_count_dev(const int32_t *tokens, const int32_t *pos_in_line, int64
                         int64_t *nnz_out, void *workspace, void *stream);
 
 /* ---- WMF ALS (cymf/wmf.pyx:136-174, cymf/linalg.pyx:144-163) ------------------------------------------- */
+/* Size limits of this section: K = num_components <= 256 for cymf_gram_*, cymf_als_cg_dev and cymf_als_half_host
+ * (the reference has no limit, wmf.pyx:44); the Cholesky change of variables (cymf_chol_transforms_dev,
+ * cymf_rows_times_matrix_*), cymf_spd_inverse_dev and the tensor-core kernels (cymf_als_rows_tc_dev,
+ * cymf_als_heavy_rows_dev) stop at K <= 128 -- above that the row systems are solved by plain CG (G passed to
+ * cymf_als_cg_dev). */
 /* G = Y^T Y (+ weight_decay * I when add_weight_decay != 0), wmf.pyx:142-143.  Y is [n, ld] of `dtype`.
  * `workspace` needs cymf_gram_workspace_doubles(n, K) doubles (per-slab partials, reduced in a fixed order so
  * the result is deterministic).  out_f64 (dense K*K doubles) and/or out_native ([ld, ld] of `dtype`, zero

@@ -125,7 +125,7 @@ def test_wmf_and_relmf_argument_validation():
     with pytest.raises(ValueError):
         cymf.WMF(prep="somewhere")
     with pytest.raises(ValueError):
-        cymf.WMF(129)
+        cymf.WMF(257)
     with pytest.raises(ValueError):
         cymf.RelMF(mode="serial")
     L = _lib.lib()

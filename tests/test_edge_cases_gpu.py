@@ -69,7 +69,26 @@ def test_wmf_any_k_and_ragged(oracle, K):
         assert _rel(m.W, Wo) <= tol and _rel(m.H, Ho) <= tol, (dtype, _rel(m.W, Wo), _rel(m.H, Ho))
         assert not m.W[0].any() and not m.H[1].any()
     with pytest.raises(ValueError):
-        cymf.WMF(129)
+        cymf.WMF(257)
+
+
+@pytest.mark.parametrize("K", [160, 256])
+def test_wmf_more_than_128_components(oracle, K):
+    """num_components > 128 (the reference has no limit, wmf.pyx:44): wide Gram kernel + plain CG, 8 elements per lane."""
+    import cymf_b200 as cymf
+    X = cymf.synth.synth_implicit(1500, 1200, 80000, seed=K)       # both dimensions well above K: Y^T Y has full rank
+    Wo, Ho = oracle.wmf_fit(X, K, 0.05, 10.0, 2)
+    for dtype, tol in (("float64", 1e-6), ("float32", 1e-4)):
+        m = cymf.WMF(K, 0.05, 10.0, dtype=dtype)
+        m.fit(X, 2, 1, verbose=False)
+        print(K, dtype, _rel(m.W, Wo), _rel(m.H, Ho))
+        assert _rel(m.W, Wo) <= tol and _rel(m.H, Ho) <= tol, (dtype, _rel(m.W, Wo), _rel(m.H, Ho))
+    W, H = Wo.copy(), Ho.copy()
+    Wn = W.copy()
+    oracle.als_half(X.indptr, X.indices, Wn, H, 0.05, 10.0)
+    m = cymf.WMF(K, 0.05, 10.0, dtype="float64")
+    m._als(X.indptr, X.indices, W, H, 1)                      # typed boundary with host buffers
+    assert _rel(W, Wn) <= 1e-6
 
 
 def test_wmf_solver_variants_agree(oracle):
