@@ -878,6 +878,7 @@ __global__ void __launch_bounds__(1024) chol_transforms_kernel(const double *__r
     const int S = K + 1;                     // padded row stride: column accesses L[j][k] spread over the banks
     double *L = sm;                          // [K][S]
     double *part = sm + K * S;               // [2][8][128] partial sums of the forward substitution
+    double *rdiag = part + 2048;             // [K] 1 / L[k][k];  [K .. K+1]: reciprocal of the next pivot (two slots)
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     for (int t = tid; t < K * K; t += blockDim.x) {
         const int i = t / K, j = t - i * K;
@@ -887,14 +888,24 @@ __global__ void __launch_bounds__(1024) chol_transforms_kernel(const double *__r
     __syncthreads();
     // Right-looking factorisation with the column scaling deferred (L D L^T form): step k only subtracts
     // l_ik l_jk / d_k from the trailing block, so one barrier per step suffices; columns are divided by sqrt(d_k)
-    // in a single pass at the end.
+    // in a single pass at the end.  The reciprocal of pivot k+1 is computed by the one thread that finishes
+    // L[k+1][k+1] during step k, so the ~200-cycle f64 division is off the other 1023 threads' critical path.
+    if (tid == 0) {
+        const double d0 = L[0];
+        if (!(d0 > 0.0) && info) *info = 1;
+        rdiag[K] = 1.0 / (d0 > 0.0 ? d0 : 1.0);
+    }
+    __syncthreads();
     for (int k = 0; k < K; ++k) {
-        const double d = L[k * S + k];
-        if (!(d > 0.0) && tid == 0 && info) *info = k + 1;
-        const double inv_d = 1.0 / (d > 0.0 ? d : 1.0);
+        const double inv_d = rdiag[K + (k & 1)];
         for (int i = k + 1 + ty; i < K; i += 32) {                 // 32 x 32 thread tile over the trailing block
             const double lik = L[i * S + k] * inv_d;
             for (int j = k + 1 + tx; j <= i; j += 32) L[i * S + j] -= lik * L[j * S + k];
+        }
+        if (tid == 0 && k + 1 < K) {                               // thread 0 has just finished L[k+1][k+1]
+            const double dn = L[(k + 1) * S + k + 1];
+            if (!(dn > 0.0) && info) *info = k + 2;
+            rdiag[K + ((k + 1) & 1)] = 1.0 / (dn > 0.0 ? dn : 1.0);
         }
         __syncthreads();
     }
@@ -903,7 +914,11 @@ __global__ void __launch_bounds__(1024) chol_transforms_kernel(const double *__r
         if (i > j) { const double dj = L[j * S + j]; L[i * S + j] = L[i * S + j] / sqrt(dj > 0.0 ? dj : 1.0); }
     }
     __syncthreads();
-    for (int k = tid; k < K; k += blockDim.x) { const double dk = L[k * S + k]; L[k * S + k] = sqrt(dk > 0.0 ? dk : 1.0); }
+    for (int k = tid; k < K; k += blockDim.x) {
+        const double dk = L[k * S + k], lk = sqrt(dk > 0.0 ? dk : 1.0);
+        L[k * S + k] = lk;
+        rdiag[k] = 1.0 / lk;
+    }
     __syncthreads();
     for (int t = tid; t < K * K; t += blockDim.x) {
         const int i = t / K, j = t - i * K;
@@ -931,7 +946,7 @@ __global__ void __launch_bounds__(1024) chol_transforms_kernel(const double *__r
             double sum = 0.0;
 #pragma unroll
             for (int g = 0; g < 8; ++g) sum += pb[g * 128 + c];
-            const double v = ((i == c ? 1.0 : 0.0) - sum) / L[i * S + i];
+            const double v = ((i == c ? 1.0 : 0.0) - sum) * rdiag[i];
 #pragma unroll
             for (int q = 0; q < 16; ++q)
                 if (q == (i >> 3)) mine[q] = v;
@@ -999,8 +1014,10 @@ __global__ void __launch_bounds__(256) rows_times_matrix_kernel(const T *in /* m
 extern "C" int cymf_chol_transforms_dev(const double *A, int32_t K, int32_t ld, double add_diag, int dtype,
                                         void *By, void *Bfwd, void *Bbwd, int32_t *info, void *stream) {
     CYMF_REQUIRE(A && By && Bfwd && Bbwd && K > 0 && K <= 128 && ld >= K && ld <= 128, "bad argument");
-    const size_t smem = sizeof(double) * ((size_t)K * (K + 1) + 2048);
+    // (A blocked variant -- 32-column panels, in-warp diagonal blocks, a dozen barriers -- was measured SLOWER: 289 us vs
+    // 235 us at K = 128, 129 vs 84 at K = 64: the serial f64 sqrt / divide chain of the pivots dominates either way.)
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = sizeof(double) * ((size_t)K * (K + 1) + 2048 + K + 2);
     if (dtype == CYMF_F32) {
         if (smem > 48 * 1024)
             CYMF_CUDA(cudaFuncSetAttribute(chol_transforms_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

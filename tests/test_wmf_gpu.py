@@ -28,9 +28,13 @@ def _csr(g):
 
 
 @pytest.mark.parametrize("name", ["wmf_small", "wmf_k64"])
-@pytest.mark.parametrize("dtype,tol", [("float64", 1e-7), ("float32", 1e-4)])
-def test_fit_matches_reference_golden(name, dtype, tol):
+@pytest.mark.parametrize("dtype,tol,short", [("float64", 1e-7, None), ("float32", 1e-4, "0"), ("float32", 1e-4, "112")])
+def test_fit_matches_reference_golden(name, dtype, tol, short, monkeypatch):
+    """short = "0": every non-empty row goes through the one-pass tensor-core solver (cymf_als_rows_tc_dev);
+    "112" (the default): rows of <= 112 entries -- all rows of these small fixtures -- take the streaming CG kernel."""
     import cymf_b200 as cymf
+    if short is not None:
+        monkeypatch.setenv("CYMF_ALS_SHORT", short)
     g = golden(name + ".npz")
     X, U, I, K = _csr(g)
     m = cymf.WMF(K, float(g["wd"]), float(g["weight"]), dtype=dtype)
@@ -151,3 +155,28 @@ def test_device_generated_matrix_normal_equations(monkeypatch):
     sess.item_half()
     assert c5_als.residuals(sess, "item", 12, seed=1) <= 1e-4
     assert sess.stats()[1] == 0                            # no row stopped at cg_max_iter
+
+
+@pytest.mark.parametrize("dtype,ld,tol", [("float32", 128, 2e-6), ("float32", 64, 2e-6), ("float64", 20, 1e-13)])
+def test_rows_times_matrix_in_place_multi_tile(dtype, ld, tol):
+    """cymf_rows_times_matrix_dev with out == in (how the warm start and the back-transform are applied) over several
+    128-row tiles: same result as out-of-place, and both match NumPy.  (tcgen05 path for f32 with ld % 32 == 0, FFMA
+    path otherwise.)"""
+    import torch
+    from cymf_b200 import _lib
+    rng = np.random.default_rng(ld)
+    rows = 1000
+    tdt = torch.float32 if dtype == "float32" else torch.float64
+    X = rng.normal(size=(rows, ld))
+    B = rng.normal(size=(ld, ld)) / np.sqrt(ld)
+    dX = torch.from_numpy(X).to("cuda", tdt)
+    dB = torch.from_numpy(B).to("cuda", tdt).contiguous()
+    out = torch.empty_like(dX)
+    code = _lib.DTYPES[dtype]
+    _lib.check(_lib.lib().cymf_rows_times_matrix_dev(_lib.ptr(dX), _lib.ptr(out), _lib.ptr(dB), code, rows, ld, None))
+    inplace = dX.clone()
+    _lib.check(_lib.lib().cymf_rows_times_matrix_dev(_lib.ptr(inplace), _lib.ptr(inplace), _lib.ptr(dB), code, rows, ld, None))
+    torch.cuda.synchronize()
+    assert torch.equal(out, inplace)
+    want = dX.double().cpu().numpy() @ dB.double().cpu().numpy()
+    assert _rel(out.double().cpu().numpy(), want) <= tol
