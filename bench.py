@@ -45,9 +45,10 @@ CPU_SAMPLE = (f"compiled reference cymf.WMF(128, 0.01, 10.0)._als (cymf/wmf.pyx:
               f"every {CPU_STRIDE}th item row of the workload with the full fixed side, all host threads; epoch time = "
               f"t_user_rows x {CPU_STRIDE} + t_item_rows x {CPU_STRIDE} (row-ratio extrapolation)")
 BPR_UNIT = "updates/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per row-solver launch from the committed ncu --set full capture
-# (profiles/, same kernel, C5-scale matrix whose fixed side does not fit L2); None until captured for this round
-ROOFLINE_TRAFFIC = None
+# dram__bytes_read.sum + dram__bytes_write.sum per row-solver launch, from the committed ncu --set full capture of this
+# command's own launches (profiles/r2_als_rows_tc_bench_ml20m_ncu_full.txt: user-side launch 0.106 GB, item-side
+# 0.580 GB; the fixed side lives in L2 at this shape, so DRAM traffic is far BELOW the algorithmic bytes)
+ROOFLINE_TRAFFIC = 0.343e9
 LR, WD, K_MAIN = 0.01, 0.01, 128
 
 
@@ -796,6 +797,7 @@ def main():
                 "gpu_launches": int(main_res["launches"]),
                 "roofline": {"bound": "hbm", "achieved": k_gbps, "peak": hbm * 1.0, "unit": "GB/s", "frac": frac,
                              "traffic": ROOFLINE_TRAFFIC, "traffic_unit": "bytes/launch",
+                             "traffic_source": "profiles/r2_als_rows_tc_bench_ml20m_ncu_full.txt (mean of the two launches of an epoch)",
                              "algorithmic_bytes_per_launch": main_res["kernel_bytes_per_launch"],
                              "sec_per_launch": main_res["kernel_sec_per_launch"],
                              "launches_timed": main_res["kernel_launches"],

@@ -37,6 +37,8 @@ int sm_count();
 bool tc_shape_ok(int dtype, int ld);
 int tc_rows_times_matrix(const float *in, float *const *outs, int n_outs, const float *B, int64_t rows, int ld,
                          cudaStream_t st);
+int tc_rows_times_matrix_tma(const float *in, float *const *outs, int n_outs, const float *B, int64_t rows, int ld,
+                             cudaStream_t st);      // tc_gemm_tma.cu; CYMF_EUNSUPPORTED if the tensor map cannot be encoded
 int64_t tc_gram_slabs(int64_t n);
 int tc_gram_partial(const float *Y, int64_t n, int K, int ld, double *partial, cudaStream_t st);
 int tc_gram_gather(const float *Y, const int64_t *indptr, const int32_t *indices, const int32_t *order,

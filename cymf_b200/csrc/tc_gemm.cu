@@ -15,6 +15,8 @@
 // is split as a = hi + lo (hi = a with the low 13 mantissa bits cleared, lo = a - hi, both exactly representable) and
 // three MMAs are issued per k-slice: hi*hi + hi*lo + lo*hi ("3xTF32"); the dropped lo*lo term is ~2^-22 relative.
 // Accumulation is f32 in TMEM.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace cymf {
@@ -225,6 +227,11 @@ bool tc_shape_ok(int dtype, int ld) { return dtype == CYMF_F32 && ld % 32 == 0 &
 
 int tc_rows_times_matrix(const float *in, float *const *outs, int n_outs, const float *B, int64_t rows, int ld,
                          cudaStream_t st) {
+    static const bool use_tma = [] { const char *v = getenv("CYMF_GEMM_TMA"); return !(v && v[0] == '0'); }();
+    if (use_tma) {                                           // TMA-fed, warp-specialised pipeline (tc_gemm_tma.cu)
+        const int rc = tc_rows_times_matrix_tma(in, outs, n_outs, B, rows, ld, st);
+        if (rc != CYMF_EUNSUPPORTED) return rc;
+    }
     tc::MultiOutF mo{};
     mo.n = n_outs;
     for (int d = 0; d < n_outs; ++d) mo.p[d] = outs[d];
