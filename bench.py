@@ -682,6 +682,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--als-only", action="store_true", help="skip the non-ALS extras (BPR, GloVe, RelMF, evaluator)")
     ap.add_argument("--glove-samples", type=int, default=100_000_000, help="co-occurrences of the GloVe extra (configs[3]: 1e8)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
@@ -747,7 +748,7 @@ def main():
                 res = {"failed": repr(ex)}
             if rank == 0:
                 extra["wmf_als_f32_k128_c5_full"] = res
-    if rank == 0 and not args.no_extra:
+    if rank == 0 and not args.no_extra and not args.als_only:
         # BPR: the other half of BASELINE.json's metric (configs[2] and the K=64 target run), one GPU
         guarded("bpr_sgd_f32_k128_c3", lambda: bpr_block(train, users, positives, 128, "sgd", "float32", x_steps, hbm,
                                                         traffic={"bytes_per_launch": 13.156e9,

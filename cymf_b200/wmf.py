@@ -255,6 +255,7 @@ class AlsSession(object):
             self.use_graph = os.environ.get("CYMF_ALS_GRAPH", "1") == "1"
         self.epochs_done = 0
         self.kernel_events = None        # set to [] to record (algorithmic bytes, start, end) CUDA events per row-solver launch
+        self.trace = None                # set to [] to record (label, event) at the phase boundaries (eager launches)
         self.h2d_bytes = self._nbytes(W) + self._nbytes(H) + 8 * (self.Ru + self.Ri + 2) + 4 * sum(self.block_nnz)
         self.d2h_bytes = self._nbytes(W) + self._nbytes(H)
 
@@ -410,6 +411,14 @@ class AlsSession(object):
             return self.dW, self.Ru, self.csr_u, self.order_u, self.classes_u, self.heavy_u, "item"
         return self.dH, self.Ri, self.csr_i, self.order_i, self.classes_i, self.heavy_i, "user"
 
+    def _mark(self, label):
+        """Dev hook (tools/als_phases.py): CUDA event at a phase boundary of the eagerly launched half sweep."""
+        if self.trace is not None:
+            import torch
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.trace.append((label, ev))
+
     def _publish(self, side):
         """This rank's block of `side`'s factor matrix has just been solved (original coordinates).  Make it the
         fixed side of the next half sweep: G = X^T X + wd I (wmf.pyx:142-143) from the ranks' K x K partials,
@@ -419,6 +428,7 @@ class AlsSession(object):
         x_blk = X_full[self.rank * R:(self.rank + 1) * R]
         stream = _lib.stream_ptr()
         es = 4 if self.dtype == _lib.F32 else 8
+        self._mark(side + ":publish start")
         if not self.dist:
             _lib.check(L.cymf_gram_dev(_lib.ptr(x_blk), self.dtype, R, K, ld, self.wd, 1, _lib.ptr(self.ws),
                                        self.ws.numel(), _lib.ptr(self.g64), None, stream))
@@ -428,15 +438,19 @@ class AlsSession(object):
             if self.peer is not None:
                 # Gram all-reduce as peer loads: barrier (all partials written), every rank sums them in rank order
                 hdl, ptrs = self.peer["gram"]
+                self._mark(side + ":gram partial")
                 hdl.barrier(channel=0)
+                self._mark(side + ":barrier 1")
                 parts = (C.c_void_p * self.world)(*ptrs)
                 _lib.check(L.cymf_gram_sum_dev(parts, self.world, K, self.wd, _lib.ptr(self.g64), stream))
             else:
                 self.dist.all_reduce(self.gpart)
                 parts = (C.c_void_p * 1)(self.gpart.data_ptr())
                 _lib.check(L.cymf_gram_sum_dev(parts, 1, K, self.wd, _lib.ptr(self.g64), stream))
+        self._mark(side + ":gram sum")
         _lib.check(L.cymf_chol_transforms_dev(_lib.ptr(self.g64), K, ld, 0.0, self.dtype, _lib.ptr(self.By),
                                               _lib.ptr(self.Bfwd), _lib.ptr(self.Bbwd), _lib.ptr(self.d_info), stream))
+        self._mark(side + ":cholesky")
         yt = self.Yt[side]
         off = self.rank * R * ld * es
         if self.peer is not None:
@@ -444,7 +458,9 @@ class AlsSession(object):
             outs = (C.c_void_p * self.world)(*[p + off for p in ptrs])
             _lib.check(L.cymf_rows_times_matrix_multi_dev(_lib.ptr(x_blk), outs, self.world, _lib.ptr(self.By),
                                                           self.dtype, R, ld, stream))
+            self._mark(side + ":transform + peer stores")
             hdl.barrier(channel=0)                               # every rank's rows have landed in this rank's Yt
+            self._mark(side + ":barrier 2")
         else:
             y_blk = yt[self.rank * R:(self.rank + 1) * R]
             _lib.check(L.cymf_rows_times_matrix_dev(_lib.ptr(x_blk), _lib.ptr(y_blk), _lib.ptr(self.By), self.dtype,
@@ -462,7 +478,9 @@ class AlsSession(object):
         es = 4 if self.dtype == _lib.F32 else 8
         stream = _lib.stream_ptr()
         # warm start in the coordinates x~ = L^T x of the fixed side's Cholesky factor
+        self._mark(side + ":solve start")
         _lib.check(L.cymf_rows_times_matrix_dev(_lib.ptr(x_blk), _lib.ptr(x_blk), _lib.ptr(self.Bfwd), self.dtype, R, ld, stream))
+        self._mark(side + ":warm start")
         main = torch.cuda.current_stream()
         start, joins, fork = 0, [], None
         if heavy:
@@ -538,9 +556,11 @@ class AlsSession(object):
                 start += count
         for done in joins:
             main.wait_event(done)
+        self._mark(side + ":row solvers")
         # back to the original coordinates (this rank's block only; the other ranks receive x~ of the NEXT transform)
         _lib.check(L.cymf_rows_times_matrix_dev(_lib.ptr(x_blk), _lib.ptr(x_blk), _lib.ptr(self.Bbwd), self.dtype, R, ld,
                                                 _lib.stream_ptr()))
+        self._mark(side + ":back transform")
         self._stale[side] = self.dist is not None
 
     def _half_transformed(self, side):
@@ -608,7 +628,7 @@ class AlsSession(object):
         import torch
         with torch.cuda.device(self.dev):
             if (self.use_graph and self.solver == "transformed" and self._pub_side == "item"
-                    and self.kernel_events is None and self.graph_error is None):
+                    and self.kernel_events is None and self.trace is None and self.graph_error is None):
                 if self._graph is None:
                     self._capture()
                 if self._graph is not None:
