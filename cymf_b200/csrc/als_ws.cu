@@ -1,0 +1,532 @@
+// als_ws.cu -- warp-specialised, persistent form of the one-pass WMF row solver (the prange body of WMF._als,
+// cymf/wmf.pyx:150-168; f32 factors in the transformed coordinates of cymf_chol_transforms_dev, ld in {32,64,96,128}).
+//
+// Same mathematics as als_tc.cu: per row S = sum_{i in row} y~_i y~_i^T (the matrix the reference accumulates entry by
+// entry, wmf.pyx:161-166) is built once on the tensor cores (3xTF32, TMEM accumulators, chains of 512 items folded in
+// registers), then (I + (w-1) S) x~ = w sum y~_i (wmf.pyx:163,168) is solved by conjugate gradient out of registers.
+// als_tc.cu runs those phases one after the other in a CTA (gather -> MMA -> fold -> ~8 CG iterations), two CTAs per
+// SM: the tensor pipe is 27-41 % busy and every phase waits on the latency of the previous one.  Here ONE CTA per SM
+// keeps all of them running at once on different rows:
+//   * warps 8-11 ("gather"): stream the 32-item chunks of the CTA's rows, row after row, through a ring of six
+//     operand stages.  cp.async (LDGSTS.128) drops each 512-byte item vector straight into the MN-major
+//     SWIZZLE_128B_BASE32B tile (als_tc6.cu's layout: an item vector IS a contiguous run of the MN dimension), four
+//     chunks ahead of their use; the raw data is the hi operand (the tensor core ignores the 13 low mantissa bits),
+//     lo = a - hi is produced by the thread that copied the piece, which also accumulates sum y~ (wmf.pyx:163);
+//   * warp 12 ("mma"): one lane issues the twelve tcgen05.mma of a chunk as soon as its stage is full, chain after
+//     chain into the FOUR 128-column TMEM accumulators, and hands stages back through tcgen05.commit;
+//   * warps 0-3 and 4-7 (two "solver" groups, thread = TMEM lane = row of S, 192 registers after setmaxnreg): take
+//     the CTA's rows alternately; fold the row's chains into registers as they complete (freeing the accumulator),
+//     then run CG with a 128-thread named barrier.  While one group iterates, the other folds / iterates on the next
+//     row and the gather + MMA warps are several rows ahead, so the tensor pipe no longer waits for anything but data.
+// Rows are assigned to CTAs on the host (cymf_als_ws_schedule_host: longest-processing-time-first over nnz + a per-row
+// constant), so every role walks the same static list and no role ever has to tell another what comes next: all
+// hand-overs are mbarrier phases whose parity follows from counters each role keeps for itself.
+#include <stdlib.h>
+
+#include <algorithm>
+#include <queue>
+#include <vector>
+
+#include "tc_common.cuh"
+
+namespace cymf {
+namespace tc {
+
+constexpr int WS_THREADS = 512;       // 4 warpgroups: solver 0, solver 1, gather, mma (+3 idle warps)
+constexpr int WS_NS = 6;              // operand stages (hi 16 KB + lo 16 KB each)
+constexpr int WS_AHEAD = 4;           // chunks gathered ahead of the conversion
+constexpr int WS_CHAIN = 16;          // 32-item chunks per accumulator chain
+constexpr int WS_NACC = 4;            // TMEM accumulators (128 columns each)
+constexpr int WS_NB = 4;              // row slots for sum y~ (gather -> solver)
+constexpr int WS_NG = 4;              // gather warps
+constexpr int WS_TILE = TILE_M * CHUNK_K;     // floats per 16 KB tile
+
+struct WsArgs {
+    const int4 *rowinfo;        // per CTA, consecutive: (row, nnz, indptr low word, indptr high word)
+    const int32_t *cta_ptr;     // [gridDim.x + 1]
+    const int32_t *indices;
+    float *X;                   // [rows, ld]  x~ rows, solved in place (warm start = current content)
+    const float *Y;             // [n, ld]     y~ rows
+    int32_t max_iter;
+    float weight, tol2;
+    unsigned long long *stats;  // [0] CG iterations summed over rows, [1] rows that hit max_iter (may be NULL)
+    unsigned long long *debug;  // [8] first timed-out wait (may be NULL): count, CTA, site, parity, three counters, thread
+};
+
+// MN-major SWIZZLE_128B_BASE32B tile of 128 (MN) x 32 (K) f32, see als_tc6.cu: byte offset of the 16-byte piece holding
+// elements m = 4 g .. 4 g + 3 of reduction index k
+__device__ __forceinline__ int ws_off(int k, int g) {
+    return (k >> 3) * 4096 + (g >> 3) * 1024 + (k & 7) * 128 + (((((g & 7) >> 1) ^ (k & 3))) << 5) + ((g & 1) << 4);
+}
+__device__ __forceinline__ uint64_t ws_desc(const void *p) {
+    return (uint64_t)((smem_u32(p) >> 4) & 0x3fffu) | ((uint64_t)(1024u >> 4) << 16) | ((uint64_t)(512u >> 4) << 32) |
+           (1ull << 46) | (1ull << 61);
+}
+__device__ __forceinline__ void ws_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ws_wait_pending(int n) {      // at most n committed groups still in flight
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    }
+}
+// mbarrier wait that sleeps in hardware between attempts: waiting warps must not eat the issue slots of working ones.
+// A wait that does not complete within ~0.5 s is a protocol failure: it is recorded in a.debug (first failure only:
+// CTA, wait site, the waiter's counters), the CTA-wide abort flag makes every later wait fall through, and the kernel
+// ends with stats[1] poisoned instead of hanging the device.
+struct WsWaitCtx {
+    volatile int *abort_flag;
+    unsigned long long *debug;
+};
+__device__ __forceinline__ bool ws_try(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void ws_wait(const WsWaitCtx &cx, uint64_t *bar, uint32_t parity, int site, uint32_t c0 = 0, uint32_t c1 = 0,
+                                        uint32_t c2 = 0) {
+    int spins = 0;
+    while (!ws_try(bar, parity)) {
+        if (++spins > 400000 || *cx.abort_flag) {
+            *cx.abort_flag = 1;
+            if (cx.debug && atomicAdd(cx.debug, 1ull) == 0ull) {
+                cx.debug[1] = blockIdx.x;
+                cx.debug[2] = (unsigned long long)site;
+                cx.debug[3] = parity;
+                cx.debug[4] = c0;
+                cx.debug[5] = c1;
+                cx.debug[6] = c2;
+                cx.debug[7] = threadIdx.x;
+            }
+            return;
+        }
+    }
+}
+__device__ __forceinline__ unsigned long long ws_sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ws_add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float ws_warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ long long ws_lo64(const int4 &ri) {
+    return (long long)(((unsigned long long)(uint32_t)ri.w << 32) | (unsigned long long)(uint32_t)ri.z);
+}
+
+struct WsShared {
+    uint64_t full[WS_NS];         // gather -> mma: all four gather warps have converted their part of the stage
+    uint64_t done[WS_NS];         // mma -> gather: the MMAs that read the stage have completed
+    uint64_t acc_full[WS_NACC];   // mma -> solver: the chain in this accumulator has completed
+    uint64_t acc_empty[WS_NACC];  // solver -> mma: the chain has been folded into registers
+    uint64_t b_full[WS_NB];       // gather -> solver: sum y~ of the row is in its slot
+    uint64_t b_free[WS_NB];       // solver -> gather: the slot has been read
+    uint32_t tmem;
+    int abort_flag;
+};
+
+template <int LD>
+__global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float *const hi_s = reinterpret_cast<float *>(smem_raw);                  // [WS_NS][4096]
+    float *const lo_s = hi_s + WS_NS * WS_TILE;                               // [WS_NS][4096]
+    float *const bq = lo_s + WS_NS * WS_TILE;                                 // [WS_NB][WS_NG][128] partial sums of y~
+    float *const p_s = bq + WS_NB * WS_NG * 128;                              // [2][128] CG direction, per solver group
+    float *const red_s = p_s + 256;                                           // [2][2][4] reduction partials
+    __shared__ WsShared sh;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = a.cta_ptr[blockIdx.x], n_rows = a.cta_ptr[blockIdx.x + 1] - row0;
+    const int4 *const rows = a.rowinfo + row0;
+
+    const WsWaitCtx cx{&sh.abort_flag, a.debug};
+    if (tid == 0) {
+        sh.abort_flag = 0;
+        for (int s = 0; s < WS_NS; ++s) { mbar_init(&sh.full[s], WS_NG); mbar_init(&sh.done[s], 1); }
+        for (int s = 0; s < WS_NACC; ++s) { mbar_init(&sh.acc_full[s], 1); mbar_init(&sh.acc_empty[s], 4); }
+        for (int s = 0; s < WS_NB; ++s) { mbar_init(&sh.b_full[s], WS_NG); mbar_init(&sh.b_free[s], 4); }
+    }
+    if (warp == 12) tmem_alloc(&sh.tmem, 512);
+    // tiles start as zeros: operand rows m >= LD (ld < 128) are never written and must read as zero
+    for (int t = tid; t < 2 * WS_NS * WS_TILE / 4; t += WS_THREADS)
+        reinterpret_cast<float4 *>(hi_s)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem0 = sh.tmem;
+    const bool dbg_on = a.debug != nullptr && blockIdx.x == 0 && lane == 0;
+#define WS_DBG(idx, val) do { if (dbg_on) a.debug[idx] = (unsigned long long)(val); } while (0)
+
+    if (warp < 8) {
+        // ================================ solver groups ======================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 192;" ::: "memory");
+        const int grp = warp >> 2, m = tid & 127, wq = warp & 3;
+        const bool m_on = m < LD;
+        const float wm1 = a.weight - 1.f;
+        float *const pg = p_s + grp * 128;
+        float *const rg = red_s + grp * 8;
+        auto gsync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); };
+        // sum over the group's 128 threads, the same value in every thread (fixed order)
+        auto gsum = [&](float v, int which) -> float {
+            v = ws_warp_sum(v);
+            if (lane == 0) rg[which * 4 + wq] = v;
+            gsync();
+            return (rg[which * 4] + rg[which * 4 + 1]) + (rg[which * 4 + 2] + rg[which * 4 + 3]);
+        };
+        // Each group owns two of the four accumulators and two of the four b slots (2 grp, 2 grp + 1) and uses them
+        // alternately, so every mbarrier has ONE waiting role that sees each of its phases in turn (a waiter that
+        // skipped a use would read the parity of the wrong phase).
+        uint32_t chain = 0, nz = 0;                              // chains / non-empty rows of THIS GROUP so far
+        for (int i = 0; i < n_rows; ++i) {
+            if ((i & 1) != grp) continue;                        // the other group's row
+            const int4 ri = rows[i];
+            const int nnz = ri.y;
+            float *const xr = a.X + (size_t)ri.x * LD;
+            if (nnz == 0) {                                      // wmf.pyx:154-156
+                if (m_on) xr[m] = 0.f;
+                continue;
+            }
+            const float x0 = m_on ? xr[m] : 0.f;                 // warm start; lands underneath the chain waits
+            const int nchains = (nnz + 32 * WS_CHAIN - 1) / (32 * WS_CHAIN);
+            unsigned long long S2[LD / 2];                       // row m of S, packed pairs
+            for (int c = 0; c < nchains; ++c, ++chain) {
+                const uint32_t acc = 2u * grp + (chain & 1u), use = chain >> 1;
+                if (wq == 0) { WS_DBG(8 + 4 * grp, i); WS_DBG(9 + 4 * grp, chain); WS_DBG(10 + 4 * grp, 1); }
+                ws_wait(cx, &sh.acc_full[acc], use & 1u, 1, chain, (uint32_t)i, (uint32_t)c);
+                if (wq == 0) WS_DBG(10 + 4 * grp, 2);
+                fence_after_sync();
+                const uint32_t t0 = tmem0 + ((uint32_t)(wq * 32) << 16) + acc * 128u;
+                if (c == 0) {
+#pragma unroll
+                    for (int q = 0; q < LD / 16; ++q) {
+                        float v[16];
+                        tmem_load16(t0 + 16 * q, v);
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) S2[8 * q + t] = pack2(v[2 * t], v[2 * t + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < LD / 16; ++q) {
+                        float v[16];
+                        tmem_load16(t0 + 16 * q, v);
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) S2[8 * q + t] = ws_add2(S2[8 * q + t], pack2(v[2 * t], v[2 * t + 1]));
+                    }
+                }
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.acc_empty[acc]);  // this warp's quarter of the accumulator is in registers
+                if (wq == 0) WS_DBG(10 + 4 * grp, 3);
+            }
+            // b = w sum y~ (four partial sums, one per gather warp, added in a fixed order)
+            const uint32_t bs = 2u * grp + (nz & 1u), buse = nz >> 1;
+            ++nz;
+            if (wq == 0) WS_DBG(10 + 4 * grp, 4);
+            ws_wait(cx, &sh.b_full[bs], buse & 1u, 2, nz, (uint32_t)i, chain);
+            if (wq == 0) WS_DBG(10 + 4 * grp, 5);
+            float b = 0.f;
+            if (m_on) {
+                const float *bp = bq + bs * (WS_NG * 128) + m;
+                b = a.weight * ((bp[0] + bp[128]) + (bp[256] + bp[384]));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.b_free[bs]);
+
+            // ---- conjugate gradient on (I + (w-1) S) x = b, row m of S in this thread's registers -----------------
+            auto matvec = [&]() -> float {                       // (S p)_m, p in shared memory
+                unsigned long long a0 = 0ull, a1 = 0ull, a2 = 0ull, a3 = 0ull;
+                const uint32_t pv = smem_u32(pg);
+                constexpr int NL = LD / 4;
+                ulonglong2 u[4];
+                auto lds = [&](ulonglong2 &d, int t) {
+                    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(d.x), "=l"(d.y) : "r"(pv + 16u * (uint32_t)t) : "memory");
+                };
+#pragma unroll
+                for (int t = 0; t < 4 && t < NL; ++t) lds(u[t], t);
+#pragma unroll
+                for (int t = 0; t < NL; ++t) {
+                    const ulonglong2 w = u[t & 3];
+                    if (t + 4 < NL) lds(u[t & 3], t + 4);
+                    if (t & 1) { fma2(a2, S2[2 * t], w.x); fma2(a3, S2[2 * t + 1], w.y); }
+                    else { fma2(a0, S2[2 * t], w.x); fma2(a1, S2[2 * t + 1], w.y); }
+                }
+                float s0, s1, s2, s3, s4, s5, s6, s7;
+                unpack2(a0, s0, s1); unpack2(a1, s2, s3); unpack2(a2, s4, s5); unpack2(a3, s6, s7);
+                return ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+            };
+            pg[m] = x0;
+            gsync();
+            float x = x0;
+            float r = b - fmaf(wm1, matvec(), x0);               // r0 = b - A x0
+            if (!m_on) r = 0.f;
+            const float bb = gsum(b * b, 0);
+            float rs = gsum(r * r, 1);
+            float p = r;
+            unsigned iters = 0;
+            bool stalled = false;
+            if (bb > 0.f) {
+                const float stop = a.tol2 * bb;
+                while (rs > stop) {
+                    if ((int)iters >= a.max_iter) { stalled = true; break; }
+                    pg[m] = p;
+                    gsync();
+                    float ap = fmaf(wm1, matvec(), p);
+                    if (!m_on) ap = 0.f;
+                    const float pAp = gsum(p * ap, 0);
+                    if (!(pAp > 0.f)) { stalled = true; break; }
+                    const float alpha = rs * rcp_approx(pAp);
+                    x = fmaf(alpha, p, x);
+                    r = fmaf(-alpha, ap, r);
+                    const float rs_new = gsum(r * r, 1);
+                    const float beta = rs_new * rcp_approx(rs);
+                    p = fmaf(beta, p, r);
+                    rs = rs_new;
+                    ++iters;
+                }
+            } else {
+                x = 0.f;                                         // b = 0  =>  x = 0
+            }
+            if (m_on) xr[m] = x;
+            if (m == 0 && a.stats) {
+                atomicAdd(a.stats, (unsigned long long)iters);
+                if (stalled) atomicAdd(a.stats + 1, 1ull);
+            }
+            gsync();                                             // pg / rg are reused by the group's next row
+            if (wq == 0) { WS_DBG(10 + 4 * grp, 6); WS_DBG(11 + 4 * grp, iters); }
+        }
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");
+        if (warp < 8 + WS_NG) {
+            // ================================ gather + convert warps =========================================
+            const int w = warp - 8;
+            const bool l_on = 4 * lane < LD;
+            uint32_t off[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) off[j] = (uint32_t)ws_off(8 * w + j, lane);
+            const float *const ysrc = a.Y + 4 * lane;
+            // gather iterator: the next chunk to copy is chunk g_c of row g_i; its eight indices for this warp are in
+            // lanes 0-7 of g_idx (loaded one step ahead)
+            int g_i = 0, g_c = 0, g_nnz = 0;
+            long long g_lo = 0;
+            int4 g_next = make_int4(0, 0, 0, 0);
+            int32_t g_idx = 0;
+            uint32_t tg = 0, tc = 0;                             // chunks copied / converted so far
+            auto g_enter = [&]() {                               // position the iterator on the first chunk of row g_i (skipping empty rows)
+                while (g_i < n_rows) {
+                    const int4 ri = g_next;
+                    g_nnz = ri.y;
+                    g_lo = ws_lo64(ri);
+                    if (g_i + 1 < n_rows) g_next = rows[g_i + 1];
+                    if (g_nnz > 0) break;
+                    ++g_i;
+                }
+                g_c = 0;
+            };
+            auto g_load_idx = [&]() {
+                const int e = 32 * g_c + 8 * w + lane;
+                g_idx = (g_i < n_rows && lane < 8 && e < g_nnz) ? __ldg(a.indices + g_lo + e) : 0;
+            };
+            if (n_rows > 0) g_next = rows[0];
+            g_enter();
+            g_load_idx();
+            // conversion iterator
+            int c_i = 0, c_c = 0, c_nnz = 0;
+            uint32_t nzg[2] = {0u, 0u};                          // non-empty rows converted so far, per solver group
+            while (c_i < n_rows && rows[c_i].y == 0) ++c_i;
+            if (c_i < n_rows) c_nnz = rows[c_i].y;
+            unsigned long long bs01 = 0ull, bs23 = 0ull;         // sum over this warp's items of elements 4 lane .. + 3
+
+            while (c_i < n_rows) {
+                if (g_i < n_rows && tg - tc < (uint32_t)WS_AHEAD) {
+                    // ---- copy one more chunk --------------------------------------------------------------------
+                    const uint32_t slot = tg % WS_NS;
+                    if (tg >= (uint32_t)WS_NS) ws_wait(cx, &sh.done[slot], (tg / WS_NS - 1) & 1u, 3, tg, tc, (uint32_t)g_i);
+                    const int left = g_nnz - 32 * g_c - 8 * w;   // items of this warp's eight that exist
+                    unsigned char *dst = reinterpret_cast<unsigned char *>(hi_s + slot * WS_TILE);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int32_t it = __shfl_sync(0xffffffffu, g_idx, j);
+                        if (l_on && j < left) cp_async16(dst + off[j], ysrc + (size_t)((uint64_t)(uint32_t)it * (uint32_t)LD));
+                    }
+                    ws_commit();
+                    ++tg;
+                    if (w == 0) WS_DBG(16, tg);
+                    if (32 * (g_c + 1) < g_nnz) ++g_c;
+                    else { ++g_i; g_enter(); }
+                    g_load_idx();
+                } else {
+                    // ---- convert the oldest copied chunk --------------------------------------------------------
+                    ws_wait_pending((int)(tg - tc) - 1);
+                    const uint32_t slot = tc % WS_NS;
+                    float *const t_hi = hi_s + slot * WS_TILE, *const t_lo = lo_s + slot * WS_TILE;
+                    const int left = c_nnz - 32 * c_c - 8 * w;
+                    if (l_on) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t o = off[j] >> 2;
+                            ulonglong2 v = make_ulonglong2(0ull, 0ull);
+                            if (j < left) v = *reinterpret_cast<const ulonglong2 *>(t_hi + o);
+                            else *reinterpret_cast<ulonglong2 *>(t_hi + o) = v;          // items past the end of the row: zeros
+                            const ulonglong2 h2 = make_ulonglong2(v.x & 0xffffe000ffffe000ull, v.y & 0xffffe000ffffe000ull);
+                            *reinterpret_cast<ulonglong2 *>(t_lo + o) = make_ulonglong2(ws_sub2(v.x, h2.x), ws_sub2(v.y, h2.y));
+                            bs01 = ws_add2(bs01, v.x);           // wmf.pyx:163
+                            bs23 = ws_add2(bs23, v.y);
+                        }
+                    }
+                    const bool row_end = 32 * (c_c + 1) >= c_nnz;
+                    if (row_end) {
+                        const int og = c_i & 1;                  // the solver group that owns this row
+                        const uint32_t nz = nzg[og], bs = 2u * og + (nz & 1u);
+                        if (nz >= 2u) ws_wait(cx, &sh.b_free[bs], ((nz >> 1) - 1) & 1u, 4, nz, tc, (uint32_t)c_i);
+                        if (l_on) *reinterpret_cast<ulonglong2 *>(bq + bs * (WS_NG * 128) + w * 128 + 4 * lane) = make_ulonglong2(bs01, bs23);
+                        bs01 = bs23 = 0ull;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sh.b_full[bs]);
+                        ++nzg[og];
+                    }
+                    fence_async_smem();                          // generic-proxy writes (cp.async, st.shared) -> tensor core
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sh.full[slot]);
+                    ++tc;
+                    if (w == 0) { WS_DBG(17, tc); WS_DBG(18, nzg[0] + nzg[1]); }
+                    if (!row_end) ++c_c;
+                    else {
+                        ++c_i;
+                        while (c_i < n_rows && rows[c_i].y == 0) ++c_i;
+                        if (c_i < n_rows) c_nnz = rows[c_i].y;
+                        c_c = 0;
+                    }
+                }
+            }
+        } else if (warp == 12) {
+            // ================================ MMA issuer ======================================================
+            const uint32_t idesc = idesc_tf32(LD) | (1u << 15) | (1u << 16);          // A and B MN-major
+            uint32_t t = 0, chg[2] = {0u, 0u};                   // chunks so far; chains so far per solver group
+            for (int i = 0; i < n_rows; ++i) {
+                const int og = i & 1;
+                const int nnz = rows[i].y;
+                const int nchunks = (nnz + 31) >> 5;
+                for (int c = 0; c < nchunks; ++c, ++t) {
+                    const uint32_t chain = chg[og];
+                    const uint32_t slot = t % WS_NS, acc = 2u * og + (chain & 1u);
+                    const bool chain_first = (c % WS_CHAIN) == 0;
+                    const bool chain_last = (c % WS_CHAIN) == WS_CHAIN - 1 || c == nchunks - 1;
+                    if (chain_first && chain >= 2u) ws_wait(cx, &sh.acc_empty[acc], ((chain >> 1) - 1) & 1u, 5, chain, t, (uint32_t)i);
+                    ws_wait(cx, &sh.full[slot], (t / WS_NS) & 1u, 6, t, chain, (uint32_t)i);
+                    if (lane == 0) {
+                        fence_after_sync();
+                        const float *t_hi = hi_s + slot * WS_TILE, *t_lo = lo_s + slot * WS_TILE;
+                        const int items = nnz - 32 * c < 32 ? nnz - 32 * c : 32;
+                        const int slices = (items + 7) >> 3;
+                        const uint32_t d = tmem0 + acc * 128u;
+                        for (int ks = 0; ks < slices; ++ks) {
+                            const uint64_t dh = ws_desc(t_hi + ks * 1024), dl = ws_desc(t_lo + ks * 1024);
+                            mma_tf32(d, dh, dl, idesc, (chain_first && ks == 0) ? 0u : 1u);      // small terms first
+                            mma_tf32(d, dl, dh, idesc, 1u);
+                            mma_tf32(d, dh, dh, idesc, 1u);
+                        }
+                        mma_commit(&sh.done[slot]);
+                        if (chain_last) mma_commit(&sh.acc_full[acc]);
+                    }
+                    __syncwarp();
+                    if (chain_last) ++chg[og];
+                    WS_DBG(20, t + 1); WS_DBG(21, chg[0] + chg[1]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && sh.abort_flag && a.stats) atomicAdd(a.stats + 1, 1ull << 40);
+    if (warp == 12) tmem_dealloc(tmem0, 512);
+}
+
+template <int LD> static int launch_ws(const WsArgs &a, int n_ctas, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((size_t)2 * WS_NS * WS_TILE + WS_NB * WS_NG * 128 + 256 + 16) + 1024;
+    auto kern = als_rows_ws_kernel<LD>;
+    CYMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CYMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    kern<<<(unsigned)n_ctas, WS_THREADS, smem, st>>>(a);
+    CYMF_LAUNCHED();
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace cymf
+
+using namespace cymf;
+
+extern "C" int32_t cymf_als_ws_ctas(void) { return (int32_t)sm_count(); }
+
+// Longest-processing-time-first assignment of rows to CTAs.  lengths need not be sorted.
+extern "C" int cymf_als_ws_schedule_host(const int64_t *indptr, const int32_t *rows, int32_t n, int32_t n_ctas,
+                                         int32_t row_cost, int32_t *cta_ptr, int32_t *rowinfo) {
+    CYMF_REQUIRE(indptr && (rows || n == 0) && cta_ptr && (rowinfo || n == 0), "null pointer");
+    CYMF_REQUIRE(n >= 0 && n_ctas > 0 && row_cost >= 0, "bad argument");
+    std::vector<int32_t> by_len(n);
+    for (int32_t j = 0; j < n; ++j) by_len[j] = j;
+    auto len = [&](int32_t j) { return indptr[rows[j] + 1] - indptr[rows[j]]; };
+    std::stable_sort(by_len.begin(), by_len.end(), [&](int32_t x, int32_t y) { return len(x) > len(y); });
+    typedef std::pair<int64_t, int32_t> Bin;                        // (load, cta): least loaded first, ties by cta id
+    std::priority_queue<Bin, std::vector<Bin>, std::greater<Bin>> heap;
+    for (int32_t b = 0; b < n_ctas; ++b) heap.push(Bin(0, b));
+    std::vector<int32_t> owner(n), count(n_ctas, 0);
+    for (int32_t k = 0; k < n; ++k) {
+        const int32_t j = by_len[k];
+        Bin top = heap.top();
+        heap.pop();
+        owner[j] = top.second;
+        ++count[top.second];
+        heap.push(Bin(top.first + len(j) + row_cost, top.second));
+    }
+    cta_ptr[0] = 0;
+    for (int32_t b = 0; b < n_ctas; ++b) cta_ptr[b + 1] = cta_ptr[b] + count[b];
+    std::vector<int32_t> fill(cta_ptr, cta_ptr + n_ctas);
+    for (int32_t k = 0; k < n; ++k) {                               // longest first inside every CTA's list
+        const int32_t j = by_len[k], pos = fill[owner[j]]++;
+        const int64_t lo = indptr[rows[j]];
+        rowinfo[4 * pos] = rows[j];
+        rowinfo[4 * pos + 1] = (int32_t)len(j);
+        rowinfo[4 * pos + 2] = (int32_t)(uint32_t)(lo & 0xffffffffll);
+        rowinfo[4 * pos + 3] = (int32_t)(uint32_t)((uint64_t)lo >> 32);
+    }
+    return 0;
+}
+
+extern "C" int cymf_als_rows_ws_dev(const int32_t *rowinfo, const int32_t *cta_ptr, int32_t n_ctas, const int32_t *indices,
+                                    void *X, const void *Y, int dtype, int32_t K, int32_t ld, double weight, double cg_tol,
+                                    int32_t cg_max_iter, unsigned long long *stats, unsigned long long *debug, void *stream) {
+    CYMF_REQUIRE(rowinfo && cta_ptr && indices && X && Y, "null pointer");
+    CYMF_REQUIRE(K > 0 && ld >= K && cg_tol > 0 && cg_max_iter > 0 && n_ctas > 0, "bad argument");
+    if (!(tc_shape_ok(dtype, ld) && tc_enabled())) {
+        set_error("als rows (warp-specialised): needs f32 factors with ld in {32, 64, 96, 128} and tcgen05 enabled");
+        return CYMF_EUNSUPPORTED;
+    }
+    tc::WsArgs a{reinterpret_cast<const int4 *>(rowinfo), cta_ptr, indices, (float *)X, (const float *)Y, cg_max_iter,
+                 (float)weight, (float)(cg_tol * cg_tol), stats, debug};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ld) {
+        case 32: return tc::launch_ws<32>(a, n_ctas, st);
+        case 64: return tc::launch_ws<64>(a, n_ctas, st);
+        case 96: return tc::launch_ws<96>(a, n_ctas, st);
+        case 128: return tc::launch_ws<128>(a, n_ctas, st);
+    }
+    set_error("als rows (warp-specialised): ld must be 32, 64, 96 or 128");
+    return CYMF_EUNSUPPORTED;
+}

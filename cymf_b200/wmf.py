@@ -177,6 +177,15 @@ class AlsSession(object):
         # row whatever its length (K x K CG from registers), so very short rows are cheaper streamed.  0 = never.
         # Measured, ml-20m shape K=128 (gpurun_out r2_sweep_v5): 13.1 ms/epoch at 0, 12.15 at 96 and 128, 12.4 at 192.
         self.short_max = int(os.environ.get("CYMF_ALS_SHORT", "112"))
+        # Rows of at most dual_max entries are solved in their dual (n x n) form, several rows per 128-slot tensor-core
+        # tile (cymf_als_rows_dual_dev); set per session below: min(128, ld) rounded down to a tile class.  When it is
+        # on, the streaming kernel is not used at all: longer rows take the one-pass K x K solver.  CYMF_ALS_DUAL=0: off.
+        self.dual_max = 0
+        # Long rows: the warp-specialised persistent solver (cymf_als_rows_ws_dev) with a host-side LPT schedule of the
+        # rows over one CTA per SM; CYMF_ALS_WS=0 falls back to the CTA-per-row kernel (cymf_als_rows_tc_dev).
+        self.use_ws = os.environ.get("CYMF_ALS_WS", "1") == "1"
+        self.ws_row_cost = int(os.environ.get("CYMF_ALS_WS_ROWCOST", "256"))
+        self._ws = {}
         self.peer_error = None
         self._unperm = {}
         self.force_width = int(force_width)
@@ -206,6 +215,9 @@ class AlsSession(object):
                 and os.environ.get("CYMF_ALS_ROWS", "tc") == "tc"):
             self.row_solver = "tc"
         self.ld = ld = (K + 31) // 32 * 32 if self.row_solver == "tc" else _lib.ld_for(K)
+        if self.row_solver == "tc" and os.environ.get("CYMF_ALS_DUAL", "1") == "1":
+            self.dual_max = 128 if ld >= 128 else (64 if ld >= 64 else 32)
+            self.dual_max = min(self.dual_max, int(os.environ.get("CYMF_ALS_DUAL_MAX", "128")))
         self.wd, self.weight = float(weight_decay), float(weight)
         self.cg_tol, self.cg_max_iter, self.stage_rows = float(cg_tol), int(cg_max_iter), int(stage_rows)
         self.prep = prep
@@ -233,8 +245,9 @@ class AlsSession(object):
             self.G = torch.empty(ld * ld, dtype=tdt, device=dev)       # [ld, ld], zero padded
             self.Ginv = torch.empty(ld * ld, dtype=tdt, device=dev)
             self.By, self.Bfwd, self.Bbwd = (torch.empty(ld * ld, dtype=tdt, device=dev) for _ in range(3))
-            self.queue = torch.zeros(4, dtype=torch.int32, device=dev)     # one work-queue head per row class
+            self.queue = torch.zeros(8, dtype=torch.int32, device=dev)     # one work-queue head per row class
             self.d_stats = torch.zeros(2, dtype=torch.int64, device=dev)
+            self.d_debug = torch.zeros(32, dtype=torch.int64, device=dev)  # first timed-out hand-over of the WS solver
             self.d_info = torch.zeros(1, dtype=torch.int32, device=dev)    # Cholesky pivot failures (checked in stats())
             # Transformed solver: every rank keeps the WHOLE fixed side in the coordinates y~ = L^-1 y (Yt["item"] is the
             # item factors as the user half sweep reads them, Yt["user"] the user factors for the item half sweep) and
@@ -404,6 +417,27 @@ class AlsSession(object):
                 heavy = (nh, first, torch.from_numpy(first).to(self.dev))
         self._n_long = getattr(self, "_n_long", {})
         self._n_long[id(blk_indptr)] = int((lengths > self.short_max).sum()) if self.short_max > 0 else n
+        self._n_dual = getattr(self, "_n_dual", {})
+        if self.dual_max > 0:                                  # lengths decrease: the dual classes are the tail of the block
+            over = int((lengths > self.dual_max).sum())
+            over64 = max(over, int((lengths > 64).sum()))
+            over32 = max(over, int((lengths > 32).sum()))
+            self._n_long[id(blk_indptr)] = over
+            self._n_dual[id(blk_indptr)] = (over64 - over, over32 - over64, n - over32)
+        if self.row_solver == "tc" and self.use_ws:
+            first, last = nh, max(self._n_long[id(blk_indptr)], nh)      # block rows [first, last) take the one-pass solver
+            if last > first:
+                n_ctas = int(self._L.cymf_als_ws_ctas())
+                ip = np.ascontiguousarray(blk_indptr.cpu().numpy(), np.int64)
+                rows = np.arange(first, last, dtype=np.int32)
+                cta_ptr = np.empty(n_ctas + 1, np.int32)
+                rowinfo = np.empty(4 * (last - first), np.int32)
+                _lib.check(self._L.cymf_als_ws_schedule_host(ip.ctypes.data_as(C.c_void_p), rows.ctypes.data_as(C.c_void_p),
+                                                             last - first, n_ctas, self.ws_row_cost,
+                                                             cta_ptr.ctypes.data_as(C.c_void_p),
+                                                             rowinfo.ctypes.data_as(C.c_void_p)))
+                self._ws[id(blk_indptr)] = (torch.from_numpy(rowinfo).to(self.dev), torch.from_numpy(cta_ptr).to(self.dev),
+                                            n_ctas)
         return (max(b16 - nh, 0), max(b8 - max(nh, b16), 0), n - max(nh, b8)), heavy
 
     def _side(self, side):
@@ -505,7 +539,9 @@ class AlsSession(object):
             n_rows = start + sum(classes)
             n_long = max(self._n_long[id(csr[0])], start)     # rows [start, n_long) one-pass, [n_long, n_rows) streamed
             count = n_long - start
-            if n_rows > n_long:
+            if n_rows > n_long and self.dual_max > 0:
+                pass                                          # launched after the long rows, below
+            elif n_rows > n_long:
                 st = self._side_streams[0] if self.overlap_classes else main
                 if st is not main:
                     if fork is None:
@@ -521,18 +557,33 @@ class AlsSession(object):
                         done = torch.cuda.Event()
                         done.record(st)
                         joins.append(done)
-            if count:
+            dual = n_rows > n_long and self.dual_max > 0
+            if count or dual:
                 if self.kernel_events is not None:
                     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     k0.record(main)
-                _lib.check(L.cymf_als_rows_tc_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order[start:]), count,
-                                                  _lib.ptr(x_blk), _lib.ptr(yt), self.dtype, K, ld, self.weight,
-                                                  self.cg_tol, self.cg_max_iter, _lib.ptr(self.queue),
-                                                  _lib.ptr(self.d_stats), stream))
+                if count and id(csr[0]) in self._ws:
+                    rowinfo, cta_ptr, n_ctas = self._ws[id(csr[0])]
+                    _lib.check(L.cymf_als_rows_ws_dev(_lib.ptr(rowinfo), _lib.ptr(cta_ptr), n_ctas, _lib.ptr(csr[1]),
+                                                      _lib.ptr(x_blk), _lib.ptr(yt), self.dtype, K, ld, self.weight,
+                                                      self.cg_tol, self.cg_max_iter, _lib.ptr(self.d_stats), _lib.ptr(self.d_debug),
+                                                      stream))
+                elif count:
+                    _lib.check(L.cymf_als_rows_tc_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order[start:]), count,
+                                                      _lib.ptr(x_blk), _lib.ptr(yt), self.dtype, K, ld, self.weight,
+                                                      self.cg_tol, self.cg_max_iter, _lib.ptr(self.queue),
+                                                      _lib.ptr(self.d_stats), stream))
+                if dual:
+                    # the short rows, behind the long ones on the same stream: 1 / 2 / 4 rows per 128-slot tile
+                    d128, d64, d32 = self._n_dual[id(csr[0])]
+                    _lib.check(L.cymf_als_rows_dual_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order[n_long:]),
+                                                        d128, d64, d32, _lib.ptr(x_blk), _lib.ptr(yt), self.dtype, K, ld,
+                                                        self.weight, self.cg_tol, self.cg_max_iter,
+                                                        _lib.ptr(self.queue[4:]), _lib.ptr(self.d_stats), stream))
                 if self.kernel_events is not None:
                     k1.record(main)
-                    # bytes this launch must move: gathered item vectors + their indices, solved rows + their indptr
-                    self.kernel_events.append((int(csr[1].numel()) * (K * es + 4) + count * (K * es + 8), k0, k1))
+                    # bytes these launches must move: gathered item vectors + their indices, solved rows + their indptr
+                    self.kernel_events.append((int(csr[1].numel()) * (K * es + 4) + (n_rows - start) * (K * es + 8), k0, k1))
         else:
             # streaming CG kernel (f64, or A/B runs): 16 warps per row for the longest rows, then 8, then 4; the
             # classes are independent (disjoint rows, own work queues), the two heavy ones go to side streams
@@ -741,6 +792,9 @@ class AlsSession(object):
             raise _lib.CymfError(f"WMF: Y^T Y + weight_decay I is not positive definite (pivot {info}); use "
                                  "weight_decay > 0 or solver='cg'")
         s = self.d_stats.cpu().numpy()
+        if int(s[1]) >> 40:                                    # the warp-specialised solver gave up on a hand-over
+            raise _lib.CymfError("WMF: internal hand-over of cymf_als_rows_ws_dev timed out (count, CTA, site, parity, "
+                                 f"counters, thread) = {self.d_debug.cpu().tolist()}; set CYMF_ALS_WS=0 and report")
         return int(s[0]), int(s[1])
 
     @property

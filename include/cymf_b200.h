@@ -328,6 +328,36 @@ int cymf_als_rows_tc_dev(const int64_t *indptr, const int32_t *indices, const in
                          void *X, const void *Y, int dtype, int32_t K, int32_t ld, double weight, double cg_tol,
                          int32_t cg_max_iter, int32_t *queue, unsigned long long *stats, void *stream);
 
+/* Warp-specialised persistent form of cymf_als_rows_tc_dev (same row system, cymf/wmf.pyx:161-168, same stopping rule
+ * and statistics): ONE 512-thread CTA per SM in which gather warps (cp.async into MN-major operand stages, four chunks
+ * ahead), an MMA-issuing warp (tcgen05 3xTF32 into four TMEM accumulators) and two solver groups (fold + CG out of
+ * registers, one thread per row of S) work on different rows at the same time.  Rows are assigned to CTAs beforehand:
+ * cymf_als_ws_schedule_host (HOST arrays; longest-processing-time-first over nnz + row_cost) fills cta_ptr[n_ctas+1]
+ * and rowinfo[4 n] = (row, nnz, indptr low word, indptr high word) per row, CTA after CTA, which the caller copies to
+ * the device for cymf_als_rows_ws_dev.  cymf_als_ws_ctas() = the CTA count to schedule for (one per SM).
+ * debug (DEVICE, 32 x u64, zeroed by the caller; may be NULL; [8..24) are progress markers of CTA 0's roles): a hand-over between the roles that does not complete
+ * within ~0.5 s is recorded there (count, CTA, wait site, parity, three counters, thread) and 2^40 is added to
+ * stats[1]; the kernel then runs to its end instead of hanging. */
+int32_t cymf_als_ws_ctas(void);
+int cymf_als_ws_schedule_host(const int64_t *indptr, const int32_t *rows, int32_t n, int32_t n_ctas, int32_t row_cost,
+                              int32_t *cta_ptr, int32_t *rowinfo);
+int cymf_als_rows_ws_dev(const int32_t *rowinfo, const int32_t *cta_ptr, int32_t n_ctas, const int32_t *indices, void *X,
+                         const void *Y, int dtype, int32_t K, int32_t ld, double weight, double cg_tol,
+                         int32_t cg_max_iter, unsigned long long *stats, unsigned long long *debug, void *stream);
+
+/* Short-row solver (f32, ld in {32,64,96,128}, transformed coordinates; rows of at most 128 entries): the same row
+ * system (cymf/wmf.pyx:161-168) in its dual form.  With Y~ the n x K matrix of the row's item vectors,
+ * x~ = weight Y~^T z where (I_n + (weight-1) Y~ Y~^T) z = 1 (push-through identity), an n x n system: Y~ Y~^T comes
+ * from ONE gather of the row (cp.async into a K-major tcgen05 operand tile, 3xTF32, TMEM accumulator), CG on it runs
+ * out of registers, and x~ is formed from the tile still in shared memory.  order[0 .. n128) are rows of 65..128
+ * entries (ld = 128 only), the next n64 rows have 33..64 entries, the last n32 rows have 0..32 (rows without entries
+ * are zeroed, wmf.pyx:154-156); one / two / four rows share a 128-row tile.  X rows are overwritten (no warm
+ * start).  queue: three int32 work-queue heads.  stats as cymf_als_cg_dev. */
+int cymf_als_rows_dual_dev(const int64_t *indptr, const int32_t *indices, const int32_t *order, int32_t n128,
+                           int32_t n64, int32_t n32, void *X, const void *Y, int dtype, int32_t K, int32_t ld,
+                           double weight, double cg_tol, int32_t cg_max_iter, int32_t *queue,
+                           unsigned long long *stats, void *stream);
+
 /* warps_per_row of cymf_als_cg_dev is 4, 8 or 16 (CTA width per row; each warp brings 8 KB of shared-memory
  * staging for the row's item vectors).  Given the row lengths in `order` (decreasing), this returns how many
  * leading rows should be solved with 16 warps and how many following ones with 8; the rest take 4. */

@@ -28,12 +28,25 @@ def _csr(g):
 
 
 @pytest.mark.parametrize("name", ["wmf_small", "wmf_k64"])
-@pytest.mark.parametrize("dtype,tol,short", [("float64", 1e-7, None), ("float32", 1e-4, "0"), ("float32", 1e-4, "112")])
+@pytest.mark.parametrize("dtype,tol,short", [("float64", 1e-7, None), ("float32", 1e-4, "0"), ("float32", 1e-4, "112"),
+                                             ("float32", 1e-4, "dual"), ("float32", 1e-4, "cta")])
 def test_fit_matches_reference_golden(name, dtype, tol, short, monkeypatch):
     """short = "0": every non-empty row goes through the one-pass tensor-core solver (cymf_als_rows_tc_dev);
-    "112" (the default): rows of <= 112 entries -- all rows of these small fixtures -- take the streaming CG kernel."""
+    "112": rows of <= 112 entries -- all rows of these small fixtures -- take the streaming CG kernel;
+    "dual" (the default): rows of <= 128 (K = 128) / 64 entries are solved in their dual form on tensor-core tiles
+    (cymf_als_rows_dual_dev), the rest by the one-pass solver."""
     import cymf_b200 as cymf
-    if short is not None:
+    if short == "dual":
+        monkeypatch.setenv("CYMF_ALS_DUAL", "1")
+    elif short == "0":
+        monkeypatch.setenv("CYMF_ALS_DUAL", "0")             # every row through the warp-specialised one-pass solver
+        monkeypatch.setenv("CYMF_ALS_SHORT", "0")
+    elif short == "cta":
+        monkeypatch.setenv("CYMF_ALS_DUAL", "0")             # ... and through the CTA-per-row form of it (als_tc.cu)
+        monkeypatch.setenv("CYMF_ALS_SHORT", "0")
+        monkeypatch.setenv("CYMF_ALS_WS", "0")
+    elif short is not None:
+        monkeypatch.setenv("CYMF_ALS_DUAL", "0")
         monkeypatch.setenv("CYMF_ALS_SHORT", short)
     g = golden(name + ".npz")
     X, U, I, K = _csr(g)
@@ -81,6 +94,102 @@ def test_gram_kernel(oracle):
             got = g64.cpu().numpy().reshape(K, K)
             assert _rel(got, want) <= tol
             assert np.array_equal(got, got.T)                  # bitwise symmetric (fixed summation order)
+
+
+@pytest.mark.parametrize("K", [32, 64, 96, 128])
+def test_dual_row_solver_against_float64(K):
+    """cymf_als_rows_dual_dev alone: rows of 0..128 entries (0..64 when ld < 128) in the three tile classes, against
+    a float64 solve of the reference's row system in the transformed coordinates,
+    (I + (w-1) sum y~ y~^T) x~ = w sum y~ (cymf/wmf.pyx:161-168 with G = I)."""
+    import torch
+    from cymf_b200 import _lib
+    rng = np.random.default_rng(K)
+    n_items, w = 5000, 10.0
+    Y = rng.normal(size=(n_items, K)) * (0.6 / np.sqrt(K))               # |y~|^2 ~ 0.36: well inside Y~ Y~^T <= I
+    top = 128 if K == 128 else 64
+    lens = np.concatenate([rng.integers(65, top + 1, 70) if top == 128 else np.empty(0, np.int64), [top, top - 1],
+                           rng.integers(33, 65, 90), [64, 33], rng.integers(0, 33, 150), [0, 1, 32, 0, 31]]).astype(np.int64)
+    lens = np.sort(lens)[::-1].copy()                                     # heaviest first, as AlsSession deals them
+    n128, n64, n32 = int((lens > 64).sum()), int(((lens > 32) & (lens <= 64)).sum()), int((lens <= 32).sum())
+    indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    indices = np.concatenate([np.sort(rng.choice(n_items, n, replace=False)) for n in lens] + [np.empty(0, np.int64)]).astype(np.int32)
+    rows = lens.shape[0]
+    want = np.zeros((rows, K))
+    for r in range(rows):
+        Yr = Y[indices[indptr[r]:indptr[r + 1]]]
+        if Yr.shape[0]:
+            want[r] = np.linalg.solve(np.eye(K) + (w - 1) * Yr.T @ Yr, w * Yr.sum(0))
+    dY = torch.from_numpy(Y).to("cuda", torch.float32).contiguous()
+    dX = torch.full((rows, K), 7.0, dtype=torch.float32, device="cuda")   # stale content must be overwritten
+    d_ip, d_ix = torch.from_numpy(indptr).cuda(), torch.from_numpy(indices).cuda()
+    order = torch.arange(rows, dtype=torch.int32, device="cuda")
+    queue = torch.zeros(4, dtype=torch.int32, device="cuda")
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    for rep in range(2):                                                  # twice: the work queues are reset per call
+        _lib.check(_lib.lib().cymf_als_rows_dual_dev(_lib.ptr(d_ip), _lib.ptr(d_ix), _lib.ptr(order), n128, n64, n32,
+                                                     _lib.ptr(dX), _lib.ptr(dY), _lib.F32, K, K, w, 1e-6, 256,
+                                                     _lib.ptr(queue), _lib.ptr(stats), None))
+        torch.cuda.synchronize()
+        got = dX.double().cpu().numpy()
+        Yf = dY.double().cpu().numpy()                                    # the f32 inputs the kernel actually saw
+        err = np.abs(got - want).max() / np.abs(want).max()
+        print(f"K={K} dual solver: rel err {err:.2e}, CG iterations/row {int(stats[0]) / rows / (rep + 1):.1f}")
+        assert err <= 2e-5
+        assert not got[lens == 0].any()
+        assert int(stats[1]) == 0
+    del Yf
+
+
+@pytest.mark.parametrize("K", [32, 64, 96, 128])
+def test_ws_row_solver_against_float64(K):
+    """cymf_als_rows_ws_dev alone (warp-specialised persistent solver + its host-side schedule): rows of 0 .. 1600
+    entries -- partial chunks, exactly one chain of 512, several chains -- from a random warm start, against a
+    float64 solve of (I + (w-1) sum y~ y~^T) x~ = w sum y~ (cymf/wmf.pyx:161-168 with G = I)."""
+    import torch
+    from cymf_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(100 + K)
+    n_items, w = 6000, 10.0
+    Y = rng.normal(size=(n_items, K))
+    Y = np.linalg.solve(np.linalg.cholesky(Y.T @ Y + 0.01 * np.eye(K)), Y.T).T          # y~ = L^-1 y: Y~^T Y~ <= I
+    lens = np.concatenate([[0, 1, 5, 31, 32, 33, 64, 100, 129, 200, 511, 512, 513, 700, 1024, 1025, 1600, 0],
+                           rng.integers(1, 400, 700)]).astype(np.int64)
+    rng.shuffle(lens)
+    indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    indices = np.concatenate([np.sort(rng.choice(n_items, n, replace=False)) for n in lens]).astype(np.int32)
+    rows = lens.shape[0]
+    want = np.zeros((rows, K))
+    for r in range(rows):
+        Yr = Y[indices[indptr[r]:indptr[r + 1]]]
+        if Yr.shape[0]:
+            want[r] = np.linalg.solve(np.eye(K) + (w - 1) * Yr.T @ Yr, w * Yr.sum(0))
+    n_ctas = int(L.cymf_als_ws_ctas())
+    assert n_ctas > 0
+    row_ids = np.arange(rows, dtype=np.int32)
+    cta_ptr, rowinfo = np.empty(n_ctas + 1, np.int32), np.empty(4 * rows, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    _lib.check(L.cymf_als_ws_schedule_host(p(indptr), p(row_ids), rows, n_ctas, 256, p(cta_ptr), p(rowinfo)))
+    assert cta_ptr[0] == 0 and cta_ptr[-1] == rows and np.array_equal(np.sort(rowinfo[0::4]), row_ids)
+    load = np.add.reduceat(np.concatenate([rowinfo[1::4] + 256, [0]]), np.minimum(cta_ptr[:-1], rows))[np.diff(cta_ptr) > 0]
+    assert load.max() <= load.min() + 1600 + 256                                        # LPT: bins differ by one row at most
+    dY = torch.from_numpy(Y).to("cuda", torch.float32).contiguous()
+    X0 = rng.normal(size=(rows, K)) * 0.05
+    dX = torch.from_numpy(X0).to("cuda", torch.float32).contiguous()
+    d_ix = torch.from_numpy(indices).cuda()
+    d_ri, d_cp = torch.from_numpy(rowinfo).cuda(), torch.from_numpy(cta_ptr).cuda()
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    debug = torch.zeros(32, dtype=torch.int64, device="cuda")
+    for rep in range(2):                                                                # second pass: warm start = the solution
+        _lib.check(L.cymf_als_rows_ws_dev(_lib.ptr(d_ri), _lib.ptr(d_cp), n_ctas, _lib.ptr(d_ix), _lib.ptr(dX), _lib.ptr(dY),
+                                          _lib.F32, K, K, w, 1e-6, 256, _lib.ptr(stats), _lib.ptr(debug), None))
+        torch.cuda.synchronize()
+        assert int(debug[0]) == 0, f"hand-over timed out: {debug.tolist()}"
+        got = dX.double().cpu().numpy()
+        err = np.abs(got - want).max() / np.abs(want).max()
+        print(f"K={K} ws solver pass {rep}: rel err {err:.2e}, CG iterations so far {int(stats[0])}")
+        assert err <= 2e-5
+        assert not got[lens == 0].any()
+        assert int(stats[1]) == 0
 
 
 def test_c2_shape_f32_within_1e4(oracle):

@@ -36,5 +36,13 @@ if s.rank == 0:
     print(f"{name} K={K} world={world}: eager epoch {tot / EPOCHS:.3f} ms on rank 0")
     for k, v in agg.items():
         print(f"   {v / EPOCHS * 1e3:9.1f} us  {k}")
+s.user_half()
+ru = s.residual("user", 24, seed=1)
+s.item_half()
+ri = s.residual("item", 24, seed=2)
+if s.rank == 0:
+    it, bad = s.stats()
+    print(f"   residual user {ru:.2e} item {ri:.2e}; dual_max {s.dual_max} short_max {s.short_max}; "
+          f"CG iterations/row/epoch {it / (s.epochs_done + 1) / (train.shape[0] + train.shape[1]):.2f}, unconverged {bad}")
 if world > 1:
     dist.destroy_process_group()
