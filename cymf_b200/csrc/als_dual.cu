@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(DUAL_THREADS, 3) als_rows_dual_kernel(const Du
             fence_async_smem();                            // generic-proxy writes (cp.async, st.shared) -> tensor core
             fence_before_sync();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {                // (not `tid == 0`: see elect_one in tc_common.cuh)
                 fence_after_sync();
 #pragma unroll
                 for (int ks = 0; ks < DUAL_KS / 8; ++ks) {

@@ -33,12 +33,13 @@ namespace cymf {
 namespace tc {
 
 constexpr int WS_THREADS = 512;       // 4 warpgroups: solver 0, solver 1, gather, mma (+3 idle warps)
-constexpr int WS_NS = 6;              // operand stages (hi 16 KB + lo 16 KB each)
-constexpr int WS_AHEAD = 4;           // chunks gathered ahead of the conversion
+constexpr int WS_NHI = 10;            // raw / hi operand slots (16 KB each): chunk t lives in slot t mod 10
+constexpr int WS_NLO = 3;             // lo operand slots (16 KB each): chunk t's lo tile lives in slot t mod 3
+constexpr int WS_NI = 2;              // copy-issuing warps (16 items of a chunk each)
 constexpr int WS_CHAIN = 16;          // 32-item chunks per accumulator chain
 constexpr int WS_NACC = 4;            // TMEM accumulators (128 columns each)
 constexpr int WS_NB = 4;              // row slots for sum y~ (gather -> solver)
-constexpr int WS_NG = 4;              // gather warps
+constexpr int WS_NG = 4;              // converter warps (8 items of a chunk each)
 constexpr int WS_TILE = TILE_M * CHUNK_K;     // floats per 16 KB tile
 
 struct WsArgs {
@@ -71,10 +72,11 @@ __device__ __forceinline__ void ws_wait_pending(int n) {      // at most n commi
         default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
     }
 }
-// mbarrier wait that sleeps in hardware between attempts: waiting warps must not eat the issue slots of working ones.
-// A wait that does not complete within ~0.5 s is a protocol failure: it is recorded in a.debug (first failure only:
-// CTA, wait site, the waiter's counters), the CTA-wide abort flag makes every later wait fall through, and the kernel
-// ends with stats[1] poisoned instead of hanging the device.
+// Hand-over waits.  mbarrier.try_wait already suspends the thread for a short, hardware-chosen time; an explicit
+// suspend-time hint compiles to NANOSLEEP loops whose wake-up latency (microseconds) is longer than a whole chunk and
+// starves the pipeline (measured), so there is none.  A wait that does not complete within ~2 s is a protocol
+// failure: it is recorded in a.debug (first failure only: CTA, wait site, the waiter's counters), the CTA-wide abort
+// flag makes every later wait fall through, and the kernel ends with stats[1] poisoned instead of hanging the device.
 struct WsWaitCtx {
     volatile int *abort_flag;
     unsigned long long *debug;
@@ -84,30 +86,40 @@ __device__ __forceinline__ bool ws_try(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ unsigned long long ws_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void ws_wait(const WsWaitCtx &cx, uint64_t *bar, uint32_t parity, int site, uint32_t c0 = 0, uint32_t c1 = 0,
                                         uint32_t c2 = 0) {
-    int spins = 0;
+    uint32_t spins = 0;
+    unsigned long long t0 = 0;
     while (!ws_try(bar, parity)) {
-        if (++spins > 400000 || *cx.abort_flag) {
-            *cx.abort_flag = 1;
-            if (cx.debug && atomicAdd(cx.debug, 1ull) == 0ull) {
-                cx.debug[1] = blockIdx.x;
-                cx.debug[2] = (unsigned long long)site;
-                cx.debug[3] = parity;
-                cx.debug[4] = c0;
-                cx.debug[5] = c1;
-                cx.debug[6] = c2;
-                cx.debug[7] = threadIdx.x;
+        if ((++spins & 1023u) == 0u) {
+            const unsigned long long now = ws_now();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 2000000000ull || *cx.abort_flag) {
+                *cx.abort_flag = 1;
+                if (cx.debug && atomicAdd(cx.debug, 1ull) == 0ull) {
+                    cx.debug[1] = blockIdx.x;
+                    cx.debug[2] = (unsigned long long)site;
+                    cx.debug[3] = parity;
+                    cx.debug[4] = c0;
+                    cx.debug[5] = c1;
+                    cx.debug[6] = c2;
+                    cx.debug[7] = threadIdx.x;
+                }
+                return;
             }
-            return;
         }
     }
 }
@@ -131,8 +143,10 @@ __device__ __forceinline__ long long ws_lo64(const int4 &ri) {
 }
 
 struct WsShared {
-    uint64_t full[WS_NS];         // gather -> mma: all four gather warps have converted their part of the stage
-    uint64_t done[WS_NS];         // mma -> gather: the MMAs that read the stage have completed
+    uint64_t landed[WS_NHI];      // copy -> convert: the chunk's item vectors are in the hi slot (cp.async completions)
+    uint64_t full[WS_NHI];        // convert -> mma: all four converter warps have produced their part of the lo tile
+    uint64_t done_hi[WS_NHI];     // mma -> copy: the MMAs that read the hi slot have completed
+    uint64_t done_lo[WS_NLO];     // mma -> convert: the MMAs that read the lo slot have completed
     uint64_t acc_full[WS_NACC];   // mma -> solver: the chain in this accumulator has completed
     uint64_t acc_empty[WS_NACC];  // solver -> mma: the chain has been folded into registers
     uint64_t b_full[WS_NB];       // gather -> solver: sum y~ of the row is in its slot
@@ -144,9 +158,9 @@ struct WsShared {
 template <int LD>
 __global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    float *const hi_s = reinterpret_cast<float *>(smem_raw);                  // [WS_NS][4096]
-    float *const lo_s = hi_s + WS_NS * WS_TILE;                               // [WS_NS][4096]
-    float *const bq = lo_s + WS_NS * WS_TILE;                                 // [WS_NB][WS_NG][128] partial sums of y~
+    float *const hi_s = reinterpret_cast<float *>(smem_raw);                  // [WS_NHI][4096]
+    float *const lo_s = hi_s + WS_NHI * WS_TILE;                              // [WS_NLO][4096]
+    float *const bq = lo_s + WS_NLO * WS_TILE;                                // [WS_NB][WS_NG][128] partial sums of y~
     float *const p_s = bq + WS_NB * WS_NG * 128;                              // [2][128] CG direction, per solver group
     float *const red_s = p_s + 256;                                           // [2][2][4] reduction partials
     __shared__ WsShared sh;
@@ -158,20 +172,28 @@ __global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs
     const WsWaitCtx cx{&sh.abort_flag, a.debug};
     if (tid == 0) {
         sh.abort_flag = 0;
-        for (int s = 0; s < WS_NS; ++s) { mbar_init(&sh.full[s], WS_NG); mbar_init(&sh.done[s], 1); }
+        for (int s = 0; s < WS_NHI; ++s) {
+            mbar_init(&sh.landed[s], 32 * WS_NI);
+            mbar_init(&sh.full[s], WS_NG);
+            mbar_init(&sh.done_hi[s], 1);
+        }
+        for (int s = 0; s < WS_NLO; ++s) mbar_init(&sh.done_lo[s], 1);
         for (int s = 0; s < WS_NACC; ++s) { mbar_init(&sh.acc_full[s], 1); mbar_init(&sh.acc_empty[s], 4); }
         for (int s = 0; s < WS_NB; ++s) { mbar_init(&sh.b_full[s], WS_NG); mbar_init(&sh.b_free[s], 4); }
     }
     if (warp == 12) tmem_alloc(&sh.tmem, 512);
     // tiles start as zeros: operand rows m >= LD (ld < 128) are never written and must read as zero
-    for (int t = tid; t < 2 * WS_NS * WS_TILE / 4; t += WS_THREADS)
+    for (int t = tid; t < (WS_NHI + WS_NLO) * WS_TILE / 4; t += WS_THREADS)
         reinterpret_cast<float4 *>(hi_s)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem0 = sh.tmem;
-    const bool dbg_on = a.debug != nullptr && blockIdx.x == 0 && lane == 0;
+    // cycle accounting of the roles of one CTA (the middle one) into debug[8..24), see tools/als_ws_prof.py
+    const bool prof = a.debug != nullptr && blockIdx.x == gridDim.x / 2;
+    const bool dbg_on = prof && lane == 0;
+    auto tick = [&]() -> uint32_t { return prof ? (uint32_t)clock() : 0u; };      // differences wrap correctly
 #define WS_DBG(idx, val) do { if (dbg_on) a.debug[idx] = (unsigned long long)(val); } while (0)
 
     if (warp < 8) {
@@ -183,34 +205,35 @@ __global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs
         float *const pg = p_s + grp * 128;
         float *const rg = red_s + grp * 8;
         auto gsync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); };
-        // sum over the group's 128 threads, the same value in every thread (fixed order)
-        auto gsum = [&](float v, int which) -> float {
-            v = ws_warp_sum(v);
-            if (lane == 0) rg[which * 4 + wq] = v;
-            gsync();
-            return (rg[which * 4] + rg[which * 4 + 1]) + (rg[which * 4 + 2] + rg[which * 4 + 3]);
-        };
         // Each group owns two of the four accumulators and two of the four b slots (2 grp, 2 grp + 1) and uses them
         // alternately, so every mbarrier has ONE waiting role that sees each of its phases in turn (a waiter that
         // skipped a use would read the parity of the wrong phase).
         uint32_t chain = 0, nz = 0;                              // chains / non-empty rows of THIS GROUP so far
-        for (int i = 0; i < n_rows; ++i) {
-            if ((i & 1) != grp) continue;                        // the other group's row
-            const int4 ri = rows[i];
+        uint32_t t_wait = 0, t_fold = 0, t_cg = 0, n_mine = 0, t_mv = 0, t_red = 0, t_pub = 0, n_it = 0;
+        // the group's next row and its warm start are fetched one row ahead (the X rows come from DRAM)
+        int4 ri_next = grp < n_rows ? rows[grp] : make_int4(0, 0, 0, 0);
+        float x0_next = (grp < n_rows && m_on) ? a.X[(size_t)ri_next.x * LD + m] : 0.f;
+        for (int i = grp; i < n_rows; i += 2) {
+            const int4 ri = ri_next;
+            const float x0 = x0_next;                            // warm start
+            if (i + 2 < n_rows) {
+                ri_next = rows[i + 2];
+                x0_next = m_on ? a.X[(size_t)ri_next.x * LD + m] : 0.f;
+            }
             const int nnz = ri.y;
             float *const xr = a.X + (size_t)ri.x * LD;
             if (nnz == 0) {                                      // wmf.pyx:154-156
                 if (m_on) xr[m] = 0.f;
                 continue;
             }
-            const float x0 = m_on ? xr[m] : 0.f;                 // warm start; lands underneath the chain waits
             const int nchains = (nnz + 32 * WS_CHAIN - 1) / (32 * WS_CHAIN);
             unsigned long long S2[LD / 2];                       // row m of S, packed pairs
             for (int c = 0; c < nchains; ++c, ++chain) {
                 const uint32_t acc = 2u * grp + (chain & 1u), use = chain >> 1;
-                if (wq == 0) { WS_DBG(8 + 4 * grp, i); WS_DBG(9 + 4 * grp, chain); WS_DBG(10 + 4 * grp, 1); }
+                const uint32_t k0 = tick();
                 ws_wait(cx, &sh.acc_full[acc], use & 1u, 1, chain, (uint32_t)i, (uint32_t)c);
-                if (wq == 0) WS_DBG(10 + 4 * grp, 2);
+                const uint32_t k1 = tick();
+                t_wait += k1 - k0;
                 fence_after_sync();
                 const uint32_t t0 = tmem0 + ((uint32_t)(wq * 32) << 16) + acc * 128u;
                 if (c == 0) {
@@ -233,14 +256,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sh.acc_empty[acc]);  // this warp's quarter of the accumulator is in registers
-                if (wq == 0) WS_DBG(10 + 4 * grp, 3);
+                t_fold += tick() - k1;
             }
             // b = w sum y~ (four partial sums, one per gather warp, added in a fixed order)
             const uint32_t bs = 2u * grp + (nz & 1u), buse = nz >> 1;
             ++nz;
-            if (wq == 0) WS_DBG(10 + 4 * grp, 4);
+            const uint32_t k2 = tick();
             ws_wait(cx, &sh.b_full[bs], buse & 1u, 2, nz, (uint32_t)i, chain);
-            if (wq == 0) WS_DBG(10 + 4 * grp, 5);
             float b = 0.f;
             if (m_on) {
                 const float *bp = bq + bs * (WS_NG * 128) + m;
@@ -254,16 +276,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs
                 unsigned long long a0 = 0ull, a1 = 0ull, a2 = 0ull, a3 = 0ull;
                 const uint32_t pv = smem_u32(pg);
                 constexpr int NL = LD / 4;
-                ulonglong2 u[4];
+                ulonglong2 u[8];                                 // eight loads in flight: shared memory is busy (MMA operands)
                 auto lds = [&](ulonglong2 &d, int t) {
                     asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(d.x), "=l"(d.y) : "r"(pv + 16u * (uint32_t)t) : "memory");
                 };
 #pragma unroll
-                for (int t = 0; t < 4 && t < NL; ++t) lds(u[t], t);
+                for (int t = 0; t < 8 && t < NL; ++t) lds(u[t], t);
 #pragma unroll
                 for (int t = 0; t < NL; ++t) {
-                    const ulonglong2 w = u[t & 3];
-                    if (t + 4 < NL) lds(u[t & 3], t + 4);
+                    const ulonglong2 w = u[t & 7];
+                    if (t + 8 < NL) lds(u[t & 7], t + 8);
                     if (t & 1) { fma2(a2, S2[2 * t], w.x); fma2(a3, S2[2 * t + 1], w.y); }
                     else { fma2(a0, S2[2 * t], w.x); fma2(a1, S2[2 * t + 1], w.y); }
                 }
@@ -271,34 +293,67 @@ __global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs
                 unpack2(a0, s0, s1); unpack2(a1, s2, s3); unpack2(a2, s4, s5); unpack2(a3, s6, s7);
                 return ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
             };
+            // Chronopoulos-Gear form of CG: the two inner products of an iteration, (r, r) and (r, A r), are taken
+            // together, so an iteration costs ONE reduction round (two interleaved shuffle butterflies + one
+            // 128-thread barrier) and one barrier for publishing r, instead of two rounds + one barrier: the rounds,
+            // not the matvec, are what an iteration waits for (measured: 43 % of the loop on the shuffle chains).
+            auto gsum2 = [&](float u, float v, float &su, float &sv) {       // sums over the group, the same in every thread
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    u += __shfl_xor_sync(0xffffffffu, u, off);
+                    v += __shfl_xor_sync(0xffffffffu, v, off);
+                }
+                if (lane == 0) *reinterpret_cast<float2 *>(rg + 2 * wq) = make_float2(u, v);
+                gsync();
+                const float4 q0 = *reinterpret_cast<const float4 *>(rg), q1 = *reinterpret_cast<const float4 *>(rg + 4);
+                su = (q0.x + q0.z) + (q1.x + q1.z);
+                sv = (q0.y + q0.w) + (q1.y + q1.w);
+            };
             pg[m] = x0;
             gsync();
             float x = x0;
             float r = b - fmaf(wm1, matvec(), x0);               // r0 = b - A x0
             if (!m_on) r = 0.f;
-            const float bb = gsum(b * b, 0);
-            float rs = gsum(r * r, 1);
-            float p = r;
+            float bb, gam;
+            gsum2(b * b, r * r, bb, gam);
             unsigned iters = 0;
             bool stalled = false;
             if (bb > 0.f) {
                 const float stop = a.tol2 * bb;
-                while (rs > stop) {
-                    if ((int)iters >= a.max_iter) { stalled = true; break; }
-                    pg[m] = p;
+                if (gam > stop) {
+                    pg[m] = r;
                     gsync();
-                    float ap = fmaf(wm1, matvec(), p);
-                    if (!m_on) ap = 0.f;
-                    const float pAp = gsum(p * ap, 0);
-                    if (!(pAp > 0.f)) { stalled = true; break; }
-                    const float alpha = rs * rcp_approx(pAp);
-                    x = fmaf(alpha, p, x);
-                    r = fmaf(-alpha, ap, r);
-                    const float rs_new = gsum(r * r, 1);
-                    const float beta = rs_new * rcp_approx(rs);
-                    p = fmaf(beta, p, r);
-                    rs = rs_new;
-                    ++iters;
+                    float w = fmaf(wm1, matvec(), r);            // w = A r
+                    if (!m_on) w = 0.f;
+                    float dlt, unused;
+                    gsum2(r * w, 0.f, dlt, unused);
+                    float p = r, sv = w;                         // s = A p
+                    float alpha = gam * rcp_approx(dlt);
+                    if (!(dlt > 0.f)) { stalled = true; alpha = 0.f; }
+                    while (!stalled) {
+                        x = fmaf(alpha, p, x);
+                        r = fmaf(-alpha, sv, r);
+                        ++iters;
+                        const uint32_t q0 = tick();
+                        pg[m] = r;
+                        gsync();
+                        const uint32_t q1 = tick();
+                        w = fmaf(wm1, matvec(), r);
+                        if (!m_on) w = 0.f;
+                        const uint32_t q2 = tick();
+                        float gam_new;
+                        gsum2(r * r, r * w, gam_new, dlt);
+                        t_pub += q1 - q0; t_mv += q2 - q1; t_red += tick() - q2; ++n_it;
+                        if (!(gam_new > stop)) break;            // converged (or NaN: leave)
+                        if ((int)iters >= a.max_iter) { stalled = true; break; }
+                        const float beta = gam_new * rcp_approx(gam);
+                        const float den = dlt - beta * gam_new * rcp_approx(alpha);
+                        if (!(den > 0.f)) { stalled = true; break; }
+                        alpha = gam_new * rcp_approx(den);
+                        p = fmaf(beta, p, r);
+                        sv = fmaf(beta, sv, w);
+                        gam = gam_new;
+                    }
                 }
             } else {
                 x = 0.f;                                         // b = 0  =>  x = 0
@@ -309,92 +364,67 @@ __global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs
                 if (stalled) atomicAdd(a.stats + 1, 1ull);
             }
             gsync();                                             // pg / rg are reused by the group's next row
-            if (wq == 0) { WS_DBG(10 + 4 * grp, 6); WS_DBG(11 + 4 * grp, iters); }
+            t_cg += tick() - k2;
+            ++n_mine;
         }
+        if (wq == 0) { WS_DBG(8 + 4 * grp, t_wait); WS_DBG(9 + 4 * grp, t_fold); WS_DBG(10 + 4 * grp, t_cg); WS_DBG(11 + 4 * grp, n_mine); }
+        if (wq == 0 && grp == 0) { WS_DBG(26, t_pub); WS_DBG(27, t_mv); WS_DBG(28, t_red); WS_DBG(29, n_it); }
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");
         if (warp < 8 + WS_NG) {
-            // ================================ gather + convert warps =========================================
+            // ================================ converter warps ================================================
+            // chunk t: wait until its vectors have landed in hi slot t mod 8 and lo slot t mod 3 is free, produce
+            // lo = a - hi for this warp's eight items, add them into sum y~, hand the stage to the MMA warp.  These
+            // warps never have a global load in flight, so the proxy fence (a full memory barrier) costs little.
             const int w = warp - 8;
             const bool l_on = 4 * lane < LD;
-            uint32_t off[8];
+            // float offset of (item 8 w + j, this lane's 16-byte piece) = offq[j & 3] + 32 j: four registers instead of eight
+            uint32_t offq[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) off[j] = (uint32_t)ws_off(8 * w + j, lane);
-            const float *const ysrc = a.Y + 4 * lane;
-            // gather iterator: the next chunk to copy is chunk g_c of row g_i; its eight indices for this warp are in
-            // lanes 0-7 of g_idx (loaded one step ahead)
-            int g_i = 0, g_c = 0, g_nnz = 0;
-            long long g_lo = 0;
-            int4 g_next = make_int4(0, 0, 0, 0);
-            int32_t g_idx = 0;
-            uint32_t tg = 0, tc = 0;                             // chunks copied / converted so far
-            auto g_enter = [&]() {                               // position the iterator on the first chunk of row g_i (skipping empty rows)
-                while (g_i < n_rows) {
-                    const int4 ri = g_next;
-                    g_nnz = ri.y;
-                    g_lo = ws_lo64(ri);
-                    if (g_i + 1 < n_rows) g_next = rows[g_i + 1];
-                    if (g_nnz > 0) break;
-                    ++g_i;
-                }
-                g_c = 0;
-            };
-            auto g_load_idx = [&]() {
-                const int e = 32 * g_c + 8 * w + lane;
-                g_idx = (g_i < n_rows && lane < 8 && e < g_nnz) ? __ldg(a.indices + g_lo + e) : 0;
-            };
-            if (n_rows > 0) g_next = rows[0];
-            g_enter();
-            g_load_idx();
-            // conversion iterator
-            int c_i = 0, c_c = 0, c_nnz = 0;
-            uint32_t nzg[2] = {0u, 0u};                          // non-empty rows converted so far, per solver group
-            while (c_i < n_rows && rows[c_i].y == 0) ++c_i;
-            if (c_i < n_rows) c_nnz = rows[c_i].y;
+            for (int q = 0; q < 4; ++q) offq[q] = (uint32_t)ws_off(8 * w + q, lane) >> 2;
+            uint32_t t = 0, nzg[2] = {0u, 0u};                   // chunks so far; non-empty rows so far per solver group
             unsigned long long bs01 = 0ull, bs23 = 0ull;         // sum over this warp's items of elements 4 lane .. + 3
-
-            while (c_i < n_rows) {
-                if (g_i < n_rows && tg - tc < (uint32_t)WS_AHEAD) {
-                    // ---- copy one more chunk --------------------------------------------------------------------
-                    const uint32_t slot = tg % WS_NS;
-                    if (tg >= (uint32_t)WS_NS) ws_wait(cx, &sh.done[slot], (tg / WS_NS - 1) & 1u, 3, tg, tc, (uint32_t)g_i);
-                    const int left = g_nnz - 32 * g_c - 8 * w;   // items of this warp's eight that exist
-                    unsigned char *dst = reinterpret_cast<unsigned char *>(hi_s + slot * WS_TILE);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int32_t it = __shfl_sync(0xffffffffu, g_idx, j);
-                        if (l_on && j < left) cp_async16(dst + off[j], ysrc + (size_t)((uint64_t)(uint32_t)it * (uint32_t)LD));
-                    }
-                    ws_commit();
-                    ++tg;
-                    if (w == 0) WS_DBG(16, tg);
-                    if (32 * (g_c + 1) < g_nnz) ++g_c;
-                    else { ++g_i; g_enter(); }
-                    g_load_idx();
-                } else {
-                    // ---- convert the oldest copied chunk --------------------------------------------------------
-                    ws_wait_pending((int)(tg - tc) - 1);
-                    const uint32_t slot = tc % WS_NS;
-                    float *const t_hi = hi_s + slot * WS_TILE, *const t_lo = lo_s + slot * WS_TILE;
-                    const int left = c_nnz - 32 * c_c - 8 * w;
+            uint32_t t_lo = 0, t_land = 0, t_bfree = 0;
+            const uint32_t g_start = tick();
+            for (int i = 0; i < n_rows; ++i) {
+                const int nnz = rows[i].y;
+                const int nchunks = (nnz + 31) >> 5;
+                for (int c = 0; c < nchunks; ++c, ++t) {
+                    const uint32_t hs = t % WS_NHI, ls = t % WS_NLO;
+                    const uint32_t k0 = tick();
+                    if (t >= (uint32_t)WS_NLO) ws_wait(cx, &sh.done_lo[ls], (t / WS_NLO - 1) & 1u, 3, t, (uint32_t)i, (uint32_t)c);
+                    const uint32_t k1 = tick();
+                    ws_wait(cx, &sh.landed[hs], (t / WS_NHI) & 1u, 7, t, (uint32_t)i, (uint32_t)c);
+                    t_lo += k1 - k0;
+                    t_land += tick() - k1;
+                    float *const t_hi = hi_s + hs * WS_TILE, *const t_lw = lo_s + ls * WS_TILE;
+                    const int left = nnz - 32 * c - 8 * w;       // items of this warp's eight that exist
                     if (l_on) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const uint32_t o = off[j] >> 2;
-                            ulonglong2 v = make_ulonglong2(0ull, 0ull);
-                            if (j < left) v = *reinterpret_cast<const ulonglong2 *>(t_hi + o);
-                            else *reinterpret_cast<ulonglong2 *>(t_hi + o) = v;          // items past the end of the row: zeros
-                            const ulonglong2 h2 = make_ulonglong2(v.x & 0xffffe000ffffe000ull, v.y & 0xffffe000ffffe000ull);
-                            *reinterpret_cast<ulonglong2 *>(t_lo + o) = make_ulonglong2(ws_sub2(v.x, h2.x), ws_sub2(v.y, h2.y));
-                            bs01 = ws_add2(bs01, v.x);           // wmf.pyx:163
-                            bs23 = ws_add2(bs23, v.y);
+                        for (int h = 0; h < 2; ++h) {            // two batches of four items: four loads in flight
+                            ulonglong2 v[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                v[q] = make_ulonglong2(0ull, 0ull);
+                                if (4 * h + q < left) v[q] = *reinterpret_cast<const ulonglong2 *>(t_hi + offq[q] + 128 * h);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t o = offq[q] + 128 * h;
+                                if (4 * h + q >= left) *reinterpret_cast<ulonglong2 *>(t_hi + o) = v[q];     // past the end of the row: zeros
+                                const ulonglong2 h2 = make_ulonglong2(v[q].x & 0xffffe000ffffe000ull, v[q].y & 0xffffe000ffffe000ull);
+                                *reinterpret_cast<ulonglong2 *>(t_lw + o) = make_ulonglong2(ws_sub2(v[q].x, h2.x), ws_sub2(v[q].y, h2.y));
+                                bs01 = ws_add2(bs01, v[q].x);    // wmf.pyx:163
+                                bs23 = ws_add2(bs23, v[q].y);
+                            }
                         }
                     }
-                    const bool row_end = 32 * (c_c + 1) >= c_nnz;
-                    if (row_end) {
-                        const int og = c_i & 1;                  // the solver group that owns this row
+                    if (c == nchunks - 1) {                      // the row's sum goes to its solver group
+                        const int og = i & 1;
                         const uint32_t nz = nzg[og], bs = 2u * og + (nz & 1u);
-                        if (nz >= 2u) ws_wait(cx, &sh.b_free[bs], ((nz >> 1) - 1) & 1u, 4, nz, tc, (uint32_t)c_i);
+                        const uint32_t k2 = tick();
+                        if (nz >= 2u) ws_wait(cx, &sh.b_free[bs], ((nz >> 1) - 1) & 1u, 4, nz, t, (uint32_t)i);
+                        t_bfree += tick() - k2;
                         if (l_on) *reinterpret_cast<ulonglong2 *>(bq + bs * (WS_NG * 128) + w * 128 + 4 * lane) = make_ulonglong2(bs01, bs23);
                         bs01 = bs23 = 0ull;
                         __syncwarp();
@@ -403,36 +433,89 @@ __global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs
                     }
                     fence_async_smem();                          // generic-proxy writes (cp.async, st.shared) -> tensor core
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sh.full[slot]);
-                    ++tc;
-                    if (w == 0) { WS_DBG(17, tc); WS_DBG(18, nzg[0] + nzg[1]); }
-                    if (!row_end) ++c_c;
-                    else {
-                        ++c_i;
-                        while (c_i < n_rows && rows[c_i].y == 0) ++c_i;
-                        if (c_i < n_rows) c_nnz = rows[c_i].y;
-                        c_c = 0;
+                    if (lane == 0) mbar_arrive(&sh.full[hs]);
+                }
+            }
+            if (w == 0) { WS_DBG(16, t_lo); WS_DBG(17, t_land); WS_DBG(18, t_bfree); WS_DBG(19, tick() - g_start); }
+        } else if (warp >= 13 && warp < 13 + WS_NI) {
+            // ================================ copy-issuing warps =============================================
+            // chunk t: as soon as hi slot t mod 8 is free, one cp.async warp instruction per item drops the 512-byte
+            // vector into its swizzled rows; the completions arrive on the slot's mbarrier by themselves
+            // (cp.async.mbarrier.arrive.noinc), so these warps never wait for data: up to eight chunks are in flight.
+            const int w = warp - 13;
+            const bool l_on = 4 * lane < LD;
+            const float *const ysrc = a.Y + 4 * lane;
+            uint32_t t = 0;
+            uint32_t t_free = 0;
+            const uint32_t c_start = tick();
+            int4 nxt = n_rows > 0 ? rows[0] : make_int4(0, 0, 0, 0);
+            int32_t idx = 0;                                     // lanes 0-15: this warp's item indices of the chunk about to be copied
+            {
+                int i2 = 0;
+                int4 r2 = nxt;
+                while (i2 < n_rows && r2.y == 0) { ++i2; if (i2 < n_rows) r2 = rows[i2]; }
+                const int e = 16 * w + lane;
+                if (i2 < n_rows && lane < 16 && e < r2.y) idx = __ldg(a.indices + ws_lo64(r2) + e);
+            }
+            for (int i = 0; i < n_rows; ++i) {
+                const int4 ri = nxt;
+                if (i + 1 < n_rows) nxt = rows[i + 1];
+                const int nnz = ri.y;
+                const long long lo = ws_lo64(ri);
+                const int nchunks = (nnz + 31) >> 5;
+                for (int c = 0; c < nchunks; ++c, ++t) {
+                    const uint32_t hs = t % WS_NHI;
+                    const uint32_t k0 = tick();
+                    if (t >= (uint32_t)WS_NHI) ws_wait(cx, &sh.done_hi[hs], (t / WS_NHI - 1) & 1u, 8, t, (uint32_t)i, (uint32_t)c);
+                    t_free += tick() - k0;
+                    const int left = nnz - 32 * c - 16 * w;
+                    unsigned char *dst = reinterpret_cast<unsigned char *>(hi_s + hs * WS_TILE);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int32_t it = __shfl_sync(0xffffffffu, idx, j);
+                        if (l_on && j < left)
+                            cp_async16(dst + ws_off(16 * w + j, lane), ysrc + (size_t)((uint64_t)(uint32_t)it * (uint32_t)LD));
+                    }
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&sh.landed[hs])) : "memory");
+                    // indices of the next chunk (of this row, or of the next non-empty row)
+                    idx = 0;
+                    if (c + 1 < nchunks) {
+                        const int e = 32 * (c + 1) + 16 * w + lane;
+                        if (lane < 16 && e < nnz) idx = __ldg(a.indices + lo + e);
+                    } else {
+                        int i2 = i + 1;
+                        int4 r2 = nxt;
+                        while (i2 < n_rows && r2.y == 0) { ++i2; if (i2 < n_rows) r2 = rows[i2]; }
+                        const int e = 16 * w + lane;
+                        if (i2 < n_rows && lane < 16 && e < r2.y) idx = __ldg(a.indices + ws_lo64(r2) + e);
                     }
                 }
             }
+            if (w == 0) { WS_DBG(24, t_free); WS_DBG(25, tick() - c_start); }
         } else if (warp == 12) {
             // ================================ MMA issuer ======================================================
             const uint32_t idesc = idesc_tf32(LD) | (1u << 15) | (1u << 16);          // A and B MN-major
             uint32_t t = 0, chg[2] = {0u, 0u};                   // chunks so far; chains so far per solver group
+            uint32_t t_empty = 0, t_full = 0;
+            const uint32_t m_start = tick();
             for (int i = 0; i < n_rows; ++i) {
                 const int og = i & 1;
                 const int nnz = rows[i].y;
                 const int nchunks = (nnz + 31) >> 5;
                 for (int c = 0; c < nchunks; ++c, ++t) {
                     const uint32_t chain = chg[og];
-                    const uint32_t slot = t % WS_NS, acc = 2u * og + (chain & 1u);
+                    const uint32_t slot = t % WS_NHI, ls = t % WS_NLO, acc = 2u * og + (chain & 1u);
                     const bool chain_first = (c % WS_CHAIN) == 0;
                     const bool chain_last = (c % WS_CHAIN) == WS_CHAIN - 1 || c == nchunks - 1;
+                    const uint32_t k0 = tick();
                     if (chain_first && chain >= 2u) ws_wait(cx, &sh.acc_empty[acc], ((chain >> 1) - 1) & 1u, 5, chain, t, (uint32_t)i);
-                    ws_wait(cx, &sh.full[slot], (t / WS_NS) & 1u, 6, t, chain, (uint32_t)i);
-                    if (lane == 0) {
+                    const uint32_t k1 = tick();
+                    ws_wait(cx, &sh.full[slot], (t / WS_NHI) & 1u, 6, t, chain, (uint32_t)i);
+                    t_empty += k1 - k0;
+                    t_full += tick() - k1;
+                    if (elect_one()) {                           // (not `lane == 0`: see tc_common.cuh)
                         fence_after_sync();
-                        const float *t_hi = hi_s + slot * WS_TILE, *t_lo = lo_s + slot * WS_TILE;
+                        const float *t_hi = hi_s + slot * WS_TILE, *t_lo = lo_s + ls * WS_TILE;
                         const int items = nnz - 32 * c < 32 ? nnz - 32 * c : 32;
                         const int slices = (items + 7) >> 3;
                         const uint32_t d = tmem0 + acc * 128u;
@@ -442,14 +525,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs
                             mma_tf32(d, dl, dh, idesc, 1u);
                             mma_tf32(d, dh, dh, idesc, 1u);
                         }
-                        mma_commit(&sh.done[slot]);
+                        mma_commit(&sh.done_hi[slot]);
+                        mma_commit(&sh.done_lo[ls]);
                         if (chain_last) mma_commit(&sh.acc_full[acc]);
                     }
                     __syncwarp();
                     if (chain_last) ++chg[og];
-                    WS_DBG(20, t + 1); WS_DBG(21, chg[0] + chg[1]);
                 }
             }
+            WS_DBG(20, t_empty); WS_DBG(21, t_full); WS_DBG(22, tick() - m_start); WS_DBG(23, t);
         }
     }
     __syncthreads();
@@ -458,7 +542,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs
 }
 
 template <int LD> static int launch_ws(const WsArgs &a, int n_ctas, cudaStream_t st) {
-    const size_t smem = sizeof(float) * ((size_t)2 * WS_NS * WS_TILE + WS_NB * WS_NG * 128 + 256 + 16) + 1024;
+    const size_t smem = sizeof(float) * ((size_t)(WS_NHI + WS_NLO) * WS_TILE + WS_NB * WS_NG * 128 + 256 + 16) + 1024;
     auto kern = als_rows_ws_kernel<LD>;
     CYMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CYMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -43,6 +43,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {      // release.cta: this thread's earlier writes are published
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One lane of a converged warp.  MMA-issuing code guarded by this (instead of `lane == 0`) lets the compiler keep the
+// descriptors in uniform registers: with a lane test it cannot tell that a single thread is active and wraps every
+// tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~100 cycles per MMA, measured in als_ws.cu).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 // all previously issued MMAs of this thread arrive on the mbarrier when they have completed
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

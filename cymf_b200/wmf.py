@@ -216,8 +216,10 @@ class AlsSession(object):
             self.row_solver = "tc"
         self.ld = ld = (K + 31) // 32 * 32 if self.row_solver == "tc" else _lib.ld_for(K)
         if self.row_solver == "tc" and os.environ.get("CYMF_ALS_DUAL", "1") == "1":
-            self.dual_max = 128 if ld >= 128 else (64 if ld >= 64 else 32)
-            self.dual_max = min(self.dual_max, int(os.environ.get("CYMF_ALS_DUAL_MAX", "128")))
+            # measured, ml-20m shape K = 128: 11.0 ms / epoch with rows of 65..128 entries in the dual kernel, 9.3 ms
+            # with those rows in the warp-specialised one-pass solver (its 128-slot tile class costs more than the K x K solve)
+            cap = 128 if ld >= 128 else (64 if ld >= 64 else 32)         # largest tile class this ld supports
+            self.dual_max = min(cap, int(os.environ.get("CYMF_ALS_DUAL_MAX", "64" if self.use_ws else "128")))
         self.wd, self.weight = float(weight_decay), float(weight)
         self.cg_tol, self.cg_max_iter, self.stage_rows = float(cg_tol), int(cg_max_iter), int(stage_rows)
         self.prep = prep
