@@ -45,10 +45,11 @@ CPU_SAMPLE = (f"compiled reference cymf.WMF(128, 0.01, 10.0)._als (cymf/wmf.pyx:
               f"every {CPU_STRIDE}th item row of the workload with the full fixed side, all host threads; epoch time = "
               f"t_user_rows x {CPU_STRIDE} + t_item_rows x {CPU_STRIDE} (row-ratio extrapolation)")
 BPR_UNIT = "updates/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per row-solver launch, from the committed ncu --set full capture of this
-# command's own launches (profiles/r2_als_rows_tc_bench_ml20m_ncu_full.txt: user-side launch 0.106 GB, item-side
-# 0.580 GB; the fixed side lives in L2 at this shape, so DRAM traffic is far BELOW the algorithmic bytes)
-ROOFLINE_TRAFFIC = 0.343e9
+# dram__bytes_read.sum + dram__bytes_write.sum of the row-solver launches of one half sweep, from the committed
+# ncu --set full capture of the same workload (profiles/r2_als_rows_ws_dual_ml20m_ncu_full.txt: user half 0.185 GB over
+# its three launches, item half 0.513 GB; the fixed side lives in L2 at this shape, so DRAM traffic is far BELOW the
+# algorithmic bytes)
+ROOFLINE_TRAFFIC = 0.349e9
 LR, WD, K_MAIN = 0.01, 0.01, 128
 
 
@@ -798,11 +799,13 @@ def main():
                 "gpu_launches": int(main_res["launches"]),
                 "roofline": {"bound": "hbm", "achieved": k_gbps, "peak": hbm * 1.0, "unit": "GB/s", "frac": frac,
                              "traffic": ROOFLINE_TRAFFIC, "traffic_unit": "bytes/launch",
-                             "traffic_source": "profiles/r2_als_rows_tc_bench_ml20m_ncu_full.txt (mean of the two launches of an epoch)",
+                             "traffic_source": "profiles/r2_als_rows_ws_dual_ml20m_ncu_full.txt: dram__bytes of the row-solver launches of one half "
+                                               "sweep (user: ws 0.149 + dual 0.020 + 0.016 GB, item: ws 0.513 GB), mean of the two",
                              "algorithmic_bytes_per_launch": main_res["kernel_bytes_per_launch"],
                              "sec_per_launch": main_res["kernel_sec_per_launch"],
                              "launches_timed": main_res["kernel_launches"],
-                             "peak_source": peak_src, "kernel": "tc::als_rows_tc_kernel<128>",
+                             "peak_source": peak_src,
+                             "kernel": "tc::als_rows_ws_kernel<128> + tc::als_rows_dual_kernel<128,{64,32}> (the row solvers of a half sweep)",
                              "per_gpu": "max-over-ranks kernel time against one GPU's peak: each rank moves its own block",
                              "epoch_algorithmic_GBps_all_gpus": main_res["bytes_per_epoch"] * args.steps / secs_all / 1e9,
                              "epoch_frac_of_aggregate_peak": main_res["bytes_per_epoch"] * args.steps / secs_all / 1e9 / (hbm * world),

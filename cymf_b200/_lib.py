@@ -87,7 +87,7 @@ SIGNATURES = {
                                          _p, _p]),
     "cymf_als_ws_ctas": (_i32, []),
     "cymf_als_ws_schedule_host": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
-    "cymf_als_rows_ws_dev": (C.c_int, [_p, _p, _i32, _p, _p, _p, C.c_int, _i32, _i32, _f64, _f64, _i32, _p, _p, _p]),
+    "cymf_als_rows_ws_dev": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i64, C.c_int, _i32, _i32, _f64, _f64, _i32, _p, _p, _p]),
     "cymf_spd_inverse_dev": (C.c_int, [_p, _i32, _i32, _f64, C.c_int, _p, _p]),
     "cymf_chol_transforms_dev": (C.c_int, [_p, _i32, _i32, _f64, C.c_int, _p, _p, _p, _p, _p]),
     "cymf_rows_times_matrix_dev": (C.c_int, [_p, _p, _p, C.c_int, _i64, _i32, _p]),

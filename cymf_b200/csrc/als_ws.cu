@@ -21,10 +21,11 @@
 // Rows are assigned to CTAs on the host (cymf_als_ws_schedule_host: longest-processing-time-first over nnz + a per-row
 // constant), so every role walks the same static list and no role ever has to tell another what comes next: all
 // hand-overs are mbarrier phases whose parity follows from counters each role keeps for itself.
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
-#include <queue>
 #include <vector>
 
 #include "tc_common.cuh"
@@ -155,8 +156,22 @@ struct WsShared {
     int abort_flag;
 };
 
-template <int LD>
-__global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs a) {
+// 4 rows x 128 bytes of the 2-D tensor `map` (rows r0..r3, columns c0 .. c0 + 31) -> 512 bytes of shared memory in the
+// map's swizzle pattern; completion is counted in bytes on `bar` (TMA tile::gather4, sm_100)
+__device__ __forceinline__ void tma_gather4(void *dst, const CUtensorMap *map, int32_t c0, int32_t r0, int32_t r1, int32_t r2,
+                                            int32_t r3, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+template <int LD, bool TMA>
+__global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs a, const __grid_constant__ CUtensorMap ymap) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float *const hi_s = reinterpret_cast<float *>(smem_raw);                  // [WS_NHI][4096]
     float *const lo_s = hi_s + WS_NHI * WS_TILE;                              // [WS_NLO][4096]
@@ -173,7 +188,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs
     if (tid == 0) {
         sh.abort_flag = 0;
         for (int s = 0; s < WS_NHI; ++s) {
-            mbar_init(&sh.landed[s], 32 * WS_NI);
+            mbar_init(&sh.landed[s], TMA ? 1 : 32 * WS_NI);
             mbar_init(&sh.full[s], WS_NG);
             mbar_init(&sh.done_hi[s], 1);
         }
@@ -276,16 +291,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs
                 unsigned long long a0 = 0ull, a1 = 0ull, a2 = 0ull, a3 = 0ull;
                 const uint32_t pv = smem_u32(pg);
                 constexpr int NL = LD / 4;
-                ulonglong2 u[8];                                 // eight loads in flight: shared memory is busy (MMA operands)
+                ulonglong2 u[4];                                 // four loads in flight (eight: no faster, measured, and spills)
                 auto lds = [&](ulonglong2 &d, int t) {
                     asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(d.x), "=l"(d.y) : "r"(pv + 16u * (uint32_t)t) : "memory");
                 };
 #pragma unroll
-                for (int t = 0; t < 8 && t < NL; ++t) lds(u[t], t);
+                for (int t = 0; t < 4 && t < NL; ++t) lds(u[t], t);
 #pragma unroll
                 for (int t = 0; t < NL; ++t) {
-                    const ulonglong2 w = u[t & 7];
-                    if (t + 8 < NL) lds(u[t & 7], t + 8);
+                    const ulonglong2 w = u[t & 3];
+                    if (t + 4 < NL) lds(u[t & 3], t + 4);
                     if (t & 1) { fma2(a2, S2[2 * t], w.x); fma2(a3, S2[2 * t + 1], w.y); }
                     else { fma2(a0, S2[2 * t], w.x); fma2(a1, S2[2 * t + 1], w.y); }
                 }
@@ -443,6 +458,72 @@ __global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs
             // vector into its swizzled rows; the completions arrive on the slot's mbarrier by themselves
             // (cp.async.mbarrier.arrive.noinc), so these warps never wait for data: up to eight chunks are in flight.
             const int w = warp - 13;
+            if constexpr (TMA) {
+                // TMA form: the two warps take the chunks alternately; one elected lane issues, per group of four items
+                // and 32-column block, ONE tile::gather4 copy (4 x 128 bytes, written in the operand's
+                // SWIZZLE_128B_BASE32B pattern by the TMA unit itself).  Bulk copies do not pass through the L1's
+                // miss tracking, whose capacity (~20 KB in flight per SM, measured) is what bounds the cp.async form.
+                uint32_t t = 0;
+                uint32_t t_free = 0;
+                const uint32_t c_start = tick();
+                int4 nxt = n_rows > 0 ? rows[0] : make_int4(0, 0, 0, 0);
+                int32_t idx = 0;                                 // lane l: index of item l of the chunk about to be copied
+                {
+                    int i2 = 0;
+                    int4 r2 = nxt;
+                    while (i2 < n_rows && r2.y == 0) { ++i2; if (i2 < n_rows) r2 = rows[i2]; }
+                    if (i2 < n_rows && lane < r2.y) idx = __ldg(a.indices + ws_lo64(r2) + lane);
+                }
+                for (int i = 0; i < n_rows; ++i) {
+                    const int4 ri = nxt;
+                    if (i + 1 < n_rows) nxt = rows[i + 1];
+                    const int nnz = ri.y;
+                    const long long lo = ws_lo64(ri);
+                    const int nchunks = (nnz + 31) >> 5;
+                    for (int c = 0; c < nchunks; ++c, ++t) {
+                        if ((int)(t & 1u) == w) {
+                            const uint32_t hs = t % WS_NHI;
+                            const uint32_t k0 = tick();
+                            if (t >= (uint32_t)WS_NHI) ws_wait(cx, &sh.done_hi[hs], (t / WS_NHI - 1) & 1u, 8, t, (uint32_t)i, (uint32_t)c);
+                            t_free += tick() - k0;
+                            const int items = nnz - 32 * c < 32 ? nnz - 32 * c : 32;
+                            const int groups = (items + 3) >> 2;
+                            unsigned char *dst = reinterpret_cast<unsigned char *>(hi_s + hs * WS_TILE);
+                            const bool leader = elect_one();
+                            if (leader) mbar_expect_tx(&sh.landed[hs], (uint32_t)(groups * (LD / 32) * 512));
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const int32_t r0 = __shfl_sync(0xffffffffu, idx, 4 * q);
+                                int32_t r1 = __shfl_sync(0xffffffffu, idx, 4 * q + 1);
+                                int32_t r2 = __shfl_sync(0xffffffffu, idx, 4 * q + 2);
+                                int32_t r3 = __shfl_sync(0xffffffffu, idx, 4 * q + 3);
+                                if (4 * q + 1 >= items) r1 = r0;          // past the end of the row: any valid row (the converter zeroes it)
+                                if (4 * q + 2 >= items) r2 = r0;
+                                if (4 * q + 3 >= items) r3 = r0;
+                                if (leader && q < groups) {
+#pragma unroll
+                                    for (int mb = 0; mb < LD / 32; ++mb)
+                                        tma_gather4(dst + (q >> 1) * 4096 + mb * 1024 + (q & 1) * 512, &ymap, 32 * mb, r0, r1, r2, r3,
+                                                    &sh.landed[hs]);
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        // indices of the next chunk (of this row, or of the next non-empty row)
+                        idx = 0;
+                        if (c + 1 < nchunks) {
+                            const int e = 32 * (c + 1) + lane;
+                            if (e < nnz) idx = __ldg(a.indices + lo + e);
+                        } else {
+                            int i2 = i + 1;
+                            int4 r2 = nxt;
+                            while (i2 < n_rows && r2.y == 0) { ++i2; if (i2 < n_rows) r2 = rows[i2]; }
+                            if (i2 < n_rows && lane < r2.y) idx = __ldg(a.indices + ws_lo64(r2) + lane);
+                        }
+                    }
+                }
+                if (w == 0) { WS_DBG(24, t_free); WS_DBG(25, tick() - c_start); }
+            } else {
             const bool l_on = 4 * lane < LD;
             const float *const ysrc = a.Y + 4 * lane;
             uint32_t t = 0;
@@ -492,6 +573,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs
                 }
             }
             if (w == 0) { WS_DBG(24, t_free); WS_DBG(25, tick() - c_start); }
+            }
         } else if (warp == 12) {
             // ================================ MMA issuer ======================================================
             const uint32_t idesc = idesc_tf32(LD) | (1u << 15) | (1u << 16);          // A and B MN-major
@@ -541,12 +623,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) als_rows_ws_kernel(const WsArgs
     if (warp == 12) tmem_dealloc(tmem0, 512);
 }
 
-template <int LD> static int launch_ws(const WsArgs &a, int n_ctas, cudaStream_t st) {
+template <int LD, bool TMA> static int launch_ws(const WsArgs &a, const CUtensorMap &ymap, int n_ctas, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)(WS_NHI + WS_NLO) * WS_TILE + WS_NB * WS_NG * 128 + 256 + 16) + 1024;
-    auto kern = als_rows_ws_kernel<LD>;
+    auto kern = als_rows_ws_kernel<LD, TMA>;
     CYMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CYMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    kern<<<(unsigned)n_ctas, WS_THREADS, smem, st>>>(a);
+    kern<<<(unsigned)n_ctas, WS_THREADS, smem, st>>>(a, ymap);
     CYMF_LAUNCHED();
     return 0;
 }
@@ -558,32 +640,52 @@ using namespace cymf;
 
 extern "C" int32_t cymf_als_ws_ctas(void) { return (int32_t)sm_count(); }
 
-// Longest-processing-time-first assignment of rows to CTAs.  lengths need not be sorted.
+// Assignment of rows to CTAs, longest rows first, in rounds: the longest unassigned rows go to the CTAs that are still
+// below the final mean load, in order of increasing load (the longest row to the least loaded CTA).  Same quality as one-row-at-a-time LPT for these
+// length distributions (loads differ by about one row), at a third of its cost (3 ms instead of 12 for 138 k rows: the
+// schedule is part of every `fit`).  lengths need not be sorted.
 extern "C" int cymf_als_ws_schedule_host(const int64_t *indptr, const int32_t *rows, int32_t n, int32_t n_ctas,
                                          int32_t row_cost, int32_t *cta_ptr, int32_t *rowinfo) {
     CYMF_REQUIRE(indptr && (rows || n == 0) && cta_ptr && (rowinfo || n == 0), "null pointer");
     CYMF_REQUIRE(n >= 0 && n_ctas > 0 && row_cost >= 0, "bad argument");
+    auto len = [&](int32_t j) { return indptr[rows[j] + 1] - indptr[rows[j]]; };
     std::vector<int32_t> by_len(n);
     for (int32_t j = 0; j < n; ++j) by_len[j] = j;
-    auto len = [&](int32_t j) { return indptr[rows[j] + 1] - indptr[rows[j]]; };
-    std::stable_sort(by_len.begin(), by_len.end(), [&](int32_t x, int32_t y) { return len(x) > len(y); });
-    typedef std::pair<int64_t, int32_t> Bin;                        // (load, cta): least loaded first, ties by cta id
-    std::priority_queue<Bin, std::vector<Bin>, std::greater<Bin>> heap;
-    for (int32_t b = 0; b < n_ctas; ++b) heap.push(Bin(0, b));
-    std::vector<int32_t> owner(n), count(n_ctas, 0);
-    for (int32_t k = 0; k < n; ++k) {
-        const int32_t j = by_len[k];
-        Bin top = heap.top();
-        heap.pop();
-        owner[j] = top.second;
-        ++count[top.second];
-        heap.push(Bin(top.first + len(j) + row_cost, top.second));
+    bool sorted = true;
+    for (int32_t j = 1; j < n && sorted; ++j) sorted = len(j - 1) >= len(j);
+    if (!sorted) std::stable_sort(by_len.begin(), by_len.end(), [&](int32_t x, int32_t y) { return len(x) > len(y); });
+    std::vector<int64_t> load(n_ctas, 0);
+    std::vector<int32_t> bins(n_ctas), owner(n), count(n_ctas, 0);
+    for (int32_t b = 0; b < n_ctas; ++b) bins[b] = b;
+    int64_t total = 0;
+    for (int32_t j = 0; j < n; ++j) total += len(j) + row_cost;
+    const int64_t mean = total / n_ctas + 1;                       // a CTA that has reached the final mean load takes no more rows
+    for (int32_t k0 = 0; k0 < n;) {
+        if (k0) std::stable_sort(bins.begin(), bins.end(), [&](int32_t x, int32_t y) { return load[x] < load[y]; });
+        int32_t k = k0;
+        for (int32_t t = 0; t < n_ctas && k < n; ++t) {
+            const int32_t b = bins[t];
+            if (t > 0 && load[b] >= mean) break;                    // (the least loaded CTA always takes one: progress)
+            const int32_t j = by_len[k++];
+            owner[j] = b;
+            ++count[b];
+            load[b] += len(j) + row_cost;
+        }
+        k0 = k;
     }
     cta_ptr[0] = 0;
     for (int32_t b = 0; b < n_ctas; ++b) cta_ptr[b + 1] = cta_ptr[b] + count[b];
-    std::vector<int32_t> fill(cta_ptr, cta_ptr + n_ctas);
-    for (int32_t k = 0; k < n; ++k) {                               // longest first inside every CTA's list
-        const int32_t j = by_len[k], pos = fill[owner[j]]++;
+    // Order inside a CTA's list: longest, shortest, second longest, second shortest, ...  The solver groups take the
+    // rows alternately, so one group folds the long rows while the other iterates on short ones, and the gather / MMA
+    // warps always have a long row to stream while a CG runs: with the list simply sorted, the long rows at its head
+    // leave the solvers idle and the short rows at its tail leave the tensor pipe idle (measured: 20 % of the solver
+    // time spent waiting for chains while the MMA warp waits for accumulators).
+    std::vector<int32_t> fill(n_ctas, 0);
+    for (int32_t k = 0; k < n; ++k) {
+        const int32_t j = by_len[k], b = owner[j], r = fill[b]++, cnt = count[b];
+        // r-th longest of cnt rows -> position 2 r (first half, from the front) or 2 (cnt - 1 - r) + 1 (second half)
+        const int32_t half = (cnt + 1) / 2;
+        const int32_t pos = cta_ptr[b] + (r < half ? 2 * r : 2 * (cnt - 1 - r) + 1);
         const int64_t lo = indptr[rows[j]];
         rowinfo[4 * pos] = rows[j];
         rowinfo[4 * pos + 1] = (int32_t)len(j);
@@ -593,9 +695,25 @@ extern "C" int cymf_als_ws_schedule_host(const int64_t *indptr, const int32_t *r
     return 0;
 }
 
+typedef CUresult (*WsEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static WsEncodeTiledFn ws_encode_tiled() {
+    static WsEncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (WsEncodeTiledFn)p;
+    }();
+    return fn;
+}
+
 extern "C" int cymf_als_rows_ws_dev(const int32_t *rowinfo, const int32_t *cta_ptr, int32_t n_ctas, const int32_t *indices,
-                                    void *X, const void *Y, int dtype, int32_t K, int32_t ld, double weight, double cg_tol,
-                                    int32_t cg_max_iter, unsigned long long *stats, unsigned long long *debug, void *stream) {
+                                    void *X, const void *Y, int64_t y_rows, int dtype, int32_t K, int32_t ld, double weight,
+                                    double cg_tol, int32_t cg_max_iter, unsigned long long *stats, unsigned long long *debug,
+                                    void *stream) {
     CYMF_REQUIRE(rowinfo && cta_ptr && indices && X && Y, "null pointer");
     CYMF_REQUIRE(K > 0 && ld >= K && cg_tol > 0 && cg_max_iter > 0 && n_ctas > 0, "bad argument");
     if (!(tc_shape_ok(dtype, ld) && tc_enabled())) {
@@ -605,11 +723,32 @@ extern "C" int cymf_als_rows_ws_dev(const int32_t *rowinfo, const int32_t *cta_p
     tc::WsArgs a{reinterpret_cast<const int4 *>(rowinfo), cta_ptr, indices, (float *)X, (const float *)Y, cg_max_iter,
                  (float)weight, (float)(cg_tol * cg_tol), stats, debug};
     cudaStream_t st = (cudaStream_t)stream;
+    // The gather goes through the TMA unit (tile::gather4: box = 32 columns x 1 row, four rows per copy, written in the
+    // operand's SWIZZLE_128B_BASE32B pattern) when the driver can encode the map; cp.async otherwise (CYMF_ALS_WS_TMA=0).
+    alignas(64) CUtensorMap ymap;
+    memset(&ymap, 0, sizeof(ymap));
+    bool tma = false;
+    // Measured (B200): both gathers deliver ~10.5 bytes per clock and SM into the swizzled tile; cp.async is 3 % faster
+    // while the fixed side lives in L2 (ml-20m shape: 9.65 vs 9.91 ms / epoch), the TMA form 1.3 % faster once it does not
+    // (3 M x 300 k x 312 M nnz: 0.1666 vs 0.1688 s / epoch).  Default: TMA for fixed sides beyond 96 MB.
+    const char *env = getenv("CYMF_ALS_WS_TMA");
+    const bool want = env ? env[0] == '1' : (double)y_rows * ld * 4.0 > 96e6;
+    if (want && y_rows > 0 && y_rows < (1ll << 31) && !((uintptr_t)Y & 15u)) {
+        if (WsEncodeTiledFn enc = ws_encode_tiled()) {
+            const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)y_rows};
+            const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+            const cuuint32_t box[2] = {32, 1};
+            const cuuint32_t estr[2] = {1, 1};
+            tma = enc(&ymap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(Y), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+    }
     switch (ld) {
-        case 32: return tc::launch_ws<32>(a, n_ctas, st);
-        case 64: return tc::launch_ws<64>(a, n_ctas, st);
-        case 96: return tc::launch_ws<96>(a, n_ctas, st);
-        case 128: return tc::launch_ws<128>(a, n_ctas, st);
+        case 32: return tma ? tc::launch_ws<32, true>(a, ymap, n_ctas, st) : tc::launch_ws<32, false>(a, ymap, n_ctas, st);
+        case 64: return tma ? tc::launch_ws<64, true>(a, ymap, n_ctas, st) : tc::launch_ws<64, false>(a, ymap, n_ctas, st);
+        case 96: return tma ? tc::launch_ws<96, true>(a, ymap, n_ctas, st) : tc::launch_ws<96, false>(a, ymap, n_ctas, st);
+        case 128: return tma ? tc::launch_ws<128, true>(a, ymap, n_ctas, st) : tc::launch_ws<128, false>(a, ymap, n_ctas, st);
     }
     set_error("als rows (warp-specialised): ld must be 32, 64, 96 or 128");
     return CYMF_EUNSUPPORTED;

@@ -567,8 +567,9 @@ class AlsSession(object):
                 if count and id(csr[0]) in self._ws:
                     rowinfo, cta_ptr, n_ctas = self._ws[id(csr[0])]
                     _lib.check(L.cymf_als_rows_ws_dev(_lib.ptr(rowinfo), _lib.ptr(cta_ptr), n_ctas, _lib.ptr(csr[1]),
-                                                      _lib.ptr(x_blk), _lib.ptr(yt), self.dtype, K, ld, self.weight,
-                                                      self.cg_tol, self.cg_max_iter, _lib.ptr(self.d_stats), _lib.ptr(self.d_debug),
+                                                      _lib.ptr(x_blk), _lib.ptr(yt), int(yt.shape[0]), self.dtype, K, ld,
+                                                      self.weight, self.cg_tol, self.cg_max_iter, _lib.ptr(self.d_stats),
+                                                      _lib.ptr(self.d_debug),
                                                       stream))
                 elif count:
                     _lib.check(L.cymf_als_rows_tc_dev(_lib.ptr(csr[0]), _lib.ptr(csr[1]), _lib.ptr(order[start:]), count,

@@ -335,6 +335,9 @@ int cymf_als_rows_tc_dev(const int64_t *indptr, const int32_t *indices, const in
  * cymf_als_ws_schedule_host (HOST arrays; longest-processing-time-first over nnz + row_cost) fills cta_ptr[n_ctas+1]
  * and rowinfo[4 n] = (row, nnz, indptr low word, indptr high word) per row, CTA after CTA, which the caller copies to
  * the device for cymf_als_rows_ws_dev.  cymf_als_ws_ctas() = the CTA count to schedule for (one per SM).
+ * y_rows = rows of Y: with it the gather runs through the TMA unit (cp.async.bulk.tensor tile::gather4 over a tensor map
+ * of Y, four item vectors per copy) when Y is larger than 96 MB or CYMF_ALS_WS_TMA=1; y_rows <= 0 or
+ * CYMF_ALS_WS_TMA=0 selects the cp.async (LDGSTS) gather.
  * debug (DEVICE, 32 x u64, zeroed by the caller; may be NULL; [8..24) are progress markers of CTA 0's roles): a hand-over between the roles that does not complete
  * within ~0.5 s is recorded there (count, CTA, wait site, parity, three counters, thread) and 2^40 is added to
  * stats[1]; the kernel then runs to its end instead of hanging. */
@@ -342,7 +345,7 @@ int32_t cymf_als_ws_ctas(void);
 int cymf_als_ws_schedule_host(const int64_t *indptr, const int32_t *rows, int32_t n, int32_t n_ctas, int32_t row_cost,
                               int32_t *cta_ptr, int32_t *rowinfo);
 int cymf_als_rows_ws_dev(const int32_t *rowinfo, const int32_t *cta_ptr, int32_t n_ctas, const int32_t *indices, void *X,
-                         const void *Y, int dtype, int32_t K, int32_t ld, double weight, double cg_tol,
+                         const void *Y, int64_t y_rows, int dtype, int32_t K, int32_t ld, double weight, double cg_tol,
                          int32_t cg_max_iter, unsigned long long *stats, unsigned long long *debug, void *stream);
 
 /* Short-row solver (f32, ld in {32,64,96,128}, transformed coordinates; rows of at most 128 entries): the same row

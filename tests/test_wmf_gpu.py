@@ -140,13 +140,16 @@ def test_dual_row_solver_against_float64(K):
     del Yf
 
 
+@pytest.mark.parametrize("gather", ["tma", "cp.async"])
 @pytest.mark.parametrize("K", [32, 64, 96, 128])
-def test_ws_row_solver_against_float64(K):
+def test_ws_row_solver_against_float64(K, gather, monkeypatch):
     """cymf_als_rows_ws_dev alone (warp-specialised persistent solver + its host-side schedule): rows of 0 .. 1600
     entries -- partial chunks, exactly one chain of 512, several chains -- from a random warm start, against a
-    float64 solve of (I + (w-1) sum y~ y~^T) x~ = w sum y~ (cymf/wmf.pyx:161-168 with G = I)."""
+    float64 solve of (I + (w-1) sum y~ y~^T) x~ = w sum y~ (cymf/wmf.pyx:161-168 with G = I).  Both gathers: through
+    the TMA unit (tile::gather4 over a tensor map of Y) and by cp.async."""
     import torch
     from cymf_b200 import _lib
+    monkeypatch.setenv("CYMF_ALS_WS_TMA", "1" if gather == "tma" else "0")
     L = _lib.lib()
     rng = np.random.default_rng(100 + K)
     n_items, w = 6000, 10.0
@@ -181,7 +184,8 @@ def test_ws_row_solver_against_float64(K):
     debug = torch.zeros(32, dtype=torch.int64, device="cuda")
     for rep in range(2):                                                                # second pass: warm start = the solution
         _lib.check(L.cymf_als_rows_ws_dev(_lib.ptr(d_ri), _lib.ptr(d_cp), n_ctas, _lib.ptr(d_ix), _lib.ptr(dX), _lib.ptr(dY),
-                                          _lib.F32, K, K, w, 1e-6, 256, _lib.ptr(stats), _lib.ptr(debug), None))
+                                          n_items, _lib.F32, K, K, w, 1e-6, 256, _lib.ptr(stats),
+                                          _lib.ptr(debug), None))
         torch.cuda.synchronize()
         assert int(debug[0]) == 0, f"hand-over timed out: {debug.tolist()}"
         got = dX.double().cpu().numpy()

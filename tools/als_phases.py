@@ -15,7 +15,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 train, _ = cymf.synth.movielens_like(name)
 W, H = init_factors(train.shape[0], train.shape[1], K)
-s = AlsSession(train, W, H, 0.01, 10.0, cg_tol=1e-6, cg_max_iter=2 * K, distributed=world > 1)
+s = AlsSession(train, W, H, 0.01, 10.0, cg_tol=float(os.environ.get('CYMF_PROBE_CGTOL', '1e-6')), cg_max_iter=2 * K, distributed=world > 1)
 for _ in range(3):
     s.epoch()
 torch.cuda.synchronize()

@@ -10,7 +10,7 @@ from cymf_b200.host import init_factors
 name, K = (sys.argv[1], int(sys.argv[2])) if len(sys.argv) > 2 else ("ml-20m", 128)
 train, _ = cymf.synth.movielens_like(name)
 W, H = init_factors(train.shape[0], train.shape[1], K)
-s = AlsSession(train, W, H, 0.01, 10.0, cg_tol=1e-6, cg_max_iter=2 * K)
+s = AlsSession(train, W, H, 0.01, 10.0, cg_tol=float(os.environ.get('CYMF_PROBE_CGTOL', '1e-6')), cg_max_iter=2 * K)
 s.use_graph = False
 for _ in range(3):
     s.epoch()
