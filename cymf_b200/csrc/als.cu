@@ -924,34 +924,39 @@ __global__ void __launch_bounds__(1024) chol_transforms_kernel(const double *__r
         const int i = t / K, j = t - i * K;
         if (i >= j) Bfwd[i * ld + j] = (T)L[i * S + j];            // L     (lower triangular)
     }
-    // L^-1 by forward substitution, all K columns at once: row i of every column needs rows < i, so rows are
-    // serial; thread (c, s) accumulates the terms j = s (mod 8) of column c and owns the entries i = s (mod 8)
-    const int c = tid & 127, sgrp = tid >> 7;
-    double mine[16];                                               // Linv[8 q + sgrp][c]
+    // L^-1 by forward substitution, column by column: column c is x with L x = e_c,
+    //     x_i = ((i == c) - sum_{c <= j < i} L[i][j] x_j) / L[i][i] ,   i = c .. K-1 .
+    // Columns are independent, so no block barrier is needed (round 1 ran all columns in lock step with one
+    // __syncthreads per row: ~110 us of the kernel's 250 at K = 128): an octet of lanes owns a column -- lane s
+    // keeps x_j for j = s (mod 8) in registers and adds its share of the sum, three shuffle steps combine the eight
+    // shares -- and a warp carries four columns, 32 warps all 128.
+    {
+        const int c = 4 * ty + (tx >> 3), s8 = tx & 7;
+        double mine[16];                                           // x_j for j = 8 q + s8
 #pragma unroll
-    for (int q = 0; q < 16; ++q) mine[q] = 0.0;
-    for (int i = 0; i < K; ++i) {
-        double acc = 0.0;
-        if (c < K && c <= i) {
+        for (int q = 0; q < 16; ++q) mine[q] = 0.0;
+        for (int i = 4 * ty; i < K; ++i) {                         // (warp-uniform bounds: the shuffles need every lane)
+            double acc = 0.0;
+            if (c < K && c <= i) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int j = 8 * q + sgrp;
-                if (j >= c && j < i) acc += L[i * S + j] * mine[q];
+                for (int q = 0; q < 16; ++q) {
+                    const int j = 8 * q + s8;
+                    if (j >= c && j < i) acc += L[i * S + j] * mine[q];
+                }
             }
-        }
-        double *pb = part + (i & 1) * 1024;
-        pb[sgrp * 128 + c] = acc;
-        __syncthreads();
-        if (sgrp == (i & 7) && c < K && c <= i) {
-            double sum = 0.0;
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            if (c < K && c <= i) {
+                const double v = ((i == c ? 1.0 : 0.0) - acc) * rdiag[i];
+                if (s8 == (i & 7)) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) sum += pb[g * 128 + c];
-            const double v = ((i == c ? 1.0 : 0.0) - sum) * rdiag[i];
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-                if (q == (i >> 3)) mine[q] = v;
-            Bbwd[i * ld + c] = (T)v;                               // L^-1  (lower triangular)
-            By[c * ld + i] = (T)v;                                 // L^-T  (upper triangular): By[k][c'] = Linv[c'][k]
+                    for (int q = 0; q < 16; ++q)
+                        if (q == (i >> 3)) mine[q] = v;
+                    Bbwd[i * ld + c] = (T)v;                       // L^-1  (lower triangular)
+                    By[c * ld + i] = (T)v;                         // L^-T  (upper triangular): By[k][c'] = Linv[c'][k]
+                }
+            }
         }
     }
 }

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) als_rows_tc_kernel(const RowSo
             // arrival on the next stage) = execution order on the tensor core.
             if (warp == (int)(issued & 7u)) {
                 mbar_wait(&mb_full[stage], (ph_full >> stage) & 1u);
-                if (lane == 0) {
+                if (elect_one()) {                                // (not `lane == 0`: see elect_one in tc_common.cuh)
                     fence_after_sync();
                     const int items = nnz - c * CHUNK_K < CHUNK_K ? nnz - c * CHUNK_K : CHUNK_K;
                     const int slices = (items + 7) >> 3;

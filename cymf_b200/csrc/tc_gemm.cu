@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(128) tc_rows_times_matrix_kernel(const float *
             }
             fence_async_smem();                      // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncthreads();
-            if (tid == 0) {
+            if (tid < 32 && elect_one()) {               // one lane of warp 0 (not `tid == 0`: see elect_one)
                 fence_after_sync();
                 // every 32-element reduction chunk gets its own accumulator (TMEM columns [kc ld, kc ld + ld)):
                 // the tensor core truncates when it adds into D, so short chains (12 MMAs) keep the f32 result
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(128) tc_gram_partial_kernel(const float *__res
         }
         fence_async_smem();
         __syncthreads();
-        if (tid == 0) {
+        if (tid < 32 && elect_one()) {                   // one lane of warp 0 (not `tid == 0`: see elect_one)
             fence_after_sync();
             // the B operand is the same tile restricted to its first ld rows (same base address, same strides)
             issue_chunk(d_tmem, t_hi, t_lo, t_hi, t_lo, groups, groups, idesc, true);

@@ -84,7 +84,7 @@ tc_rows_times_matrix_tma_kernel(const __grid_constant__ CUtensorMap in_map, cons
     const int64_t n_tiles = (rows + TILE_M - 1) / TILE_M;
 
     if (warp == 8) {                                              // ---- TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t cg = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
                 for (int kc = 0; kc < nk; ++kc, ++cg) {
@@ -95,7 +95,7 @@ tc_rows_times_matrix_tma_kernel(const __grid_constant__ CUtensorMap in_map, cons
                 }
         }
     } else if (warp == 9) {                                       // ---- MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {                                        // (not `lane == 0`: see elect_one in tc_common.cuh)
             const uint32_t idesc = idesc_tf32(ld);
             const uint32_t lbo_b = b_groups * 128;
             uint32_t cg = 0, lt = 0;

@@ -13,8 +13,14 @@ from oracle import oracle
 X = cymf.synth.synth_implicit(300, 220, 9000, seed=7).tolil()
 X[2, :] = 1
 X = X.tocsr()
-for K, dtype, short in ((32, "float32", "0"), (64, "float32", "112"), (20, "float64", "112")):
-    os.environ["CYMF_ALS_SHORT"] = short
+# (K, dtype, environment): default = dual-form tiles for rows of <= 64 entries + warp-specialised one-pass solver (cp.async
+# gather); then the same solver with the TMA tile::gather4 copy path; the CTA-per-row solver; the streaming CG kernel
+for K, dtype, env in ((32, "float32", {}), (64, "float32", {"CYMF_ALS_WS_TMA": "1", "CYMF_ALS_DUAL": "0"}),
+                      (64, "float32", {"CYMF_ALS_WS": "0", "CYMF_ALS_DUAL": "0", "CYMF_ALS_SHORT": "0"}), (20, "float64", {})):
+    for k in ("CYMF_ALS_WS_TMA", "CYMF_ALS_DUAL", "CYMF_ALS_WS", "CYMF_ALS_SHORT"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    short = env
     Wo, Ho = oracle.wmf_fit(X, K, 0.01, 10.0, 2)
     m = cymf.WMF(K, 0.01, 10.0, dtype=dtype)
     m.fit(X, 2, 1, verbose=False)
