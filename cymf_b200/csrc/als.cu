@@ -1016,12 +1016,205 @@ __global__ void __launch_bounds__(256) rows_times_matrix_kernel(const T *in /* m
     }
 }
 
+// Blocked form of the same computation (G = L L^T, outputs L, L^-1, L^-T), 256 threads: thread (bi, bj) owns the 8 x 8
+// block of rows 8 bi .., columns 8 bj .. IN REGISTERS.  The unblocked kernel above spends ~1.5 us on each of its 128
+// barrier-separated column steps whatever the work; here a step is a block column:
+//   (a) the diagonal thread factorises its 8 x 8 block and inverts the triangular factor (the only sqrt / divide chain),
+//       hidden behind the other warps' trailing update of the previous step;
+//   (b) the panel threads form L_ik = A_ik L_kk^-T; (c) the trailing threads subtract L_ik L_jk^T -- two barriers per step.
+// L^-1 follows right-looking as well: once block row t of X = L^-1 is complete, every block below adds L_it X_tj to its
+// accumulator, and X_ij = -L_ii^-1 acc_ij when its own row comes up.  Rows / columns past K are padded with the identity.
+template <typename T>
+__global__ void __launch_bounds__(256) chol_transforms_blocked_kernel(const double *__restrict__ A, int K, int ld, double add_diag,
+                                                                      T *__restrict__ By, T *__restrict__ Bfwd,
+                                                                      T *__restrict__ Bbwd, int *__restrict__ info) {
+    extern __shared__ double sm[];
+    double *Lb = sm;                         // [16][16][64] blocks of L (lower block triangle used)
+    double *Wall = Lb + 16 * 16 * 64;        // [16][64] inverses of the diagonal blocks of L
+    double *XR = Wall + 16 * 64;             // [16][64] the block row of L^-1 that has just been completed
+    const int tid = threadIdx.x, bi = tid >> 4, bj = tid & 15;
+    const int NB = (K + 7) >> 3;
+    const bool lower = bi >= bj && bi < NB;
+    for (int t = tid; t < ld * ld; t += 256) { By[t] = T(0); Bfwd[t] = T(0); Bbwd[t] = T(0); }
+    double a[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int i = 8 * bi + r, j = 8 * bj + c;
+            a[r][c] = (lower && i < K && j < K) ? A[(size_t)i * K + j] + (i == j ? add_diag : 0.0) : (i == j ? 1.0 : 0.0);
+        }
+    // (a): factor this thread's (diagonal) block in place -> lower triangle of a = L_kk, w = L_kk^-1, both published
+    auto factor_diag = [&](int kb) {
+        double w[8][8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            double d = a[c][c];
+#pragma unroll
+            for (int t = 0; t < c; ++t) d -= a[c][t] * a[c][t];
+            if (!(d > 0.0)) { if (info) *info = 8 * kb + c + 1; d = 1.0; }
+            const double l = sqrt(d), rl = 1.0 / l;
+            a[c][c] = l;
+#pragma unroll
+            for (int r = c + 1; r < 8; ++r) {
+                double v = a[r][c];
+#pragma unroll
+                for (int t = 0; t < c; ++t) v -= a[r][t] * a[c][t];
+                a[r][c] = v * rl;
+            }
+#pragma unroll
+            for (int r = 0; r < c; ++r) a[r][c] = 0.0;
+            // row c of the inverse: w[c][c] = 1 / l, w[c][j] = -(sum_{t=j}^{c-1} l[c][t] w[t][j]) / l for j < c
+            w[c][c] = rl;
+#pragma unroll
+            for (int j = 0; j < c; ++j) {
+                double v = 0.0;
+#pragma unroll
+                for (int t = j; t < c; ++t) v += a[c][t] * w[t][j];
+                w[c][j] = -v * rl;
+            }
+#pragma unroll
+            for (int j = c + 1; j < 8; ++j) w[c][j] = 0.0;
+        }
+        double *lw = Lb + (kb * 16 + kb) * 64, *ww = Wall + kb * 64;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { lw[8 * r + c] = a[r][c]; ww[8 * r + c] = w[r][c]; }
+    };
+    if (bi == 0 && bj == 0) factor_diag(0);
+    __syncthreads();
+    for (int kb = 0; kb < NB; ++kb) {
+        if (bj == kb && bi > kb && bi < NB) {                      // (b) panel: L_ik = A_ik W_k^T
+            const double *ww = Wall + kb * 64;
+            double l[8][8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                double wc[8];
+#pragma unroll
+                for (int t = 0; t <= c; ++t) wc[t] = ww[8 * c + t];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int t = 0; t <= c; ++t) v += a[r][t] * wc[t];
+                    l[r][c] = v;
+                }
+            }
+            double *lw = Lb + (bi * 16 + kb) * 64;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) lw[8 * r + c] = l[r][c];
+        }
+        __syncthreads();
+        if (bj > kb && lower) {                                    // (c) trailing update: A_ij -= L_ik L_jk^T
+            const double *li = Lb + (bi * 16 + kb) * 64, *lj = Lb + (bj * 16 + kb) * 64;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                double x[8], y[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) { x[r] = li[8 * r + t]; y[r] = lj[8 * r + t]; }
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) a[r][c] -= x[r] * y[c];
+            }
+            if (bi == kb + 1 && bj == kb + 1) factor_diag(kb + 1);   // next step's (a), under the other warps' updates
+        }
+        __syncthreads();
+    }
+    // L (lower triangular) -> Bfwd
+    if (lower) {
+        const double *lw = Lb + (bi * 16 + bj) * 64;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int i = 8 * bi + r, j = 8 * bj + c;
+                if (i < K && j <= i) Bfwd[i * ld + j] = (T)lw[8 * r + c];
+            }
+    }
+    // X = L^-1, block row by block row; a[][] now accumulates sum_t L_it X_tj for this thread's block
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[r][c] = 0.0;
+    for (int t = 0; t < NB; ++t) {
+        if (bi == t && bj <= t) {
+            const double *ww = Wall + t * 64;
+            double x[8][8];
+            if (bj == t) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) x[r][c] = ww[8 * r + c];
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    double wr[8];
+#pragma unroll
+                    for (int q = 0; q <= r; ++q) wr[q] = ww[8 * r + q];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int q = 0; q <= r; ++q) v += wr[q] * a[q][c];
+                        x[r][c] = -v;
+                    }
+                }
+            }
+            double *xw = XR + bj * 64;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    xw[8 * r + c] = x[r][c];
+                    const int i = 8 * t + r, j = 8 * bj + c;
+                    if (i < K && j <= i) {
+                        Bbwd[i * ld + j] = (T)x[r][c];              // L^-1  (lower triangular)
+                        By[j * ld + i] = (T)x[r][c];                // L^-T  (upper triangular)
+                    }
+                }
+        }
+        __syncthreads();
+        if (bi > t && bi < NB && bj <= t) {                         // acc_ij += L_it X_tj
+            const double *li = Lb + (bi * 16 + t) * 64, *xj = XR + bj * 64;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                double x[8], y[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) { x[r] = li[8 * r + q]; y[r] = xj[8 * q + r]; }
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) a[r][c] += x[r] * y[c];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 extern "C" int cymf_chol_transforms_dev(const double *A, int32_t K, int32_t ld, double add_diag, int dtype,
                                         void *By, void *Bfwd, void *Bbwd, int32_t *info, void *stream) {
     CYMF_REQUIRE(A && By && Bfwd && Bbwd && K > 0 && K <= 128 && ld >= K && ld <= 128, "bad argument");
     // (A blocked variant -- 32-column panels, in-warp diagonal blocks, a dozen barriers -- was measured SLOWER: 289 us vs
     // 235 us at K = 128, 129 vs 84 at K = 64: the serial f64 sqrt / divide chain of the pivots dominates either way.)
     cudaStream_t st = (cudaStream_t)stream;
+    // ... until the blocks were kept in REGISTERS (chol_transforms_blocked_kernel); CYMF_CHOL_BLOCKED=0 selects the unblocked kernel
+    const char *env = getenv("CYMF_CHOL_BLOCKED");
+    if (!(env && env[0] == '0')) {
+        const size_t bsm = sizeof(double) * (16 * 16 * 64 + 2 * 16 * 64);
+        if (dtype == CYMF_F32) {
+            CYMF_CUDA(cudaFuncSetAttribute(chol_transforms_blocked_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+            chol_transforms_blocked_kernel<float><<<1, 256, bsm, st>>>(A, K, ld, add_diag, (float *)By, (float *)Bfwd, (float *)Bbwd, info);
+        } else {
+            CYMF_CUDA(cudaFuncSetAttribute(chol_transforms_blocked_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+            chol_transforms_blocked_kernel<double><<<1, 256, bsm, st>>>(A, K, ld, add_diag, (double *)By, (double *)Bfwd, (double *)Bbwd, info);
+        }
+        CYMF_LAUNCHED();
+        return 0;
+    }
     const size_t smem = sizeof(double) * ((size_t)K * (K + 1) + 2048 + K + 2);
     if (dtype == CYMF_F32) {
         if (smem > 48 * 1024)
