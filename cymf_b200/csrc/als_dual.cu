@@ -1,4 +1,4 @@
-// als_dual.cu -- WMF ALS row solver for SHORT rows (n <= 128 entries): the prange body of WMF._als
+// als_dual.cu -- WMF ALS row solver for SHORT rows (n <= 128 entries; AlsSession sends it the rows of <= 64): the prange body of WMF._als
 // (cymf/wmf.pyx:150-168) solved in its dual (n x n) form, f32 factors with ld in {32, 64, 96, 128}.
 //
 // In the coordinates y~ = L^-1 y, x~ = L^T x (G = L L^T, cymf_chol_transforms_dev) the reference's row system

@@ -7,20 +7,30 @@
 // als_tc.cu runs those phases one after the other in a CTA (gather -> MMA -> fold -> ~8 CG iterations), two CTAs per
 // SM: the tensor pipe is 27-41 % busy and every phase waits on the latency of the previous one.  Here ONE CTA per SM
 // keeps all of them running at once on different rows:
-//   * warps 8-11 ("gather"): stream the 32-item chunks of the CTA's rows, row after row, through a ring of six
-//     operand stages.  cp.async (LDGSTS.128) drops each 512-byte item vector straight into the MN-major
-//     SWIZZLE_128B_BASE32B tile (als_tc6.cu's layout: an item vector IS a contiguous run of the MN dimension), four
-//     chunks ahead of their use; the raw data is the hi operand (the tensor core ignores the 13 low mantissa bits),
-//     lo = a - hi is produced by the thread that copied the piece, which also accumulates sum y~ (wmf.pyx:163);
-//   * warp 12 ("mma"): one lane issues the twelve tcgen05.mma of a chunk as soon as its stage is full, chain after
-//     chain into the FOUR 128-column TMEM accumulators, and hands stages back through tcgen05.commit;
+//   * warps 13-14 ("copy"): stream the 32-item chunks of the CTA's rows, row after row, into a ring of ten 16 KB "hi"
+//     slots as soon as a slot is free.  Either cp.async (LDGSTS.128: one warp instruction drops a 512-byte item vector
+//     straight into the MN-major SWIZZLE_128B_BASE32B tile of als_tc6.cu -- an item vector IS a contiguous run of the MN
+//     dimension -- and the completions arrive on the slot's mbarrier by themselves, cp.async.mbarrier.arrive.noinc), or
+//     the TMA unit (cp.async.bulk.tensor tile::gather4 over a tensor map of Y whose swizzle mode is the operand's own
+//     pattern: four item vectors per copy, complete_tx bytes on the same mbarrier).  These warps never wait for data and
+//     never execute a proxy fence (which would wait for their copies in flight: measured, that alone cost the first
+//     version of this kernel its look-ahead);
+//   * warps 8-11 ("convert"): when a chunk has landed, produce lo = a - hi into one of three 16 KB "lo" slots (the raw
+//     data is the hi operand: the tensor core ignores the 13 low mantissa bits), add the items into sum y~
+//     (wmf.pyx:163), fence.proxy.async, hand the stage to the MMA warp;
+//   * warp 12 ("mma"): one ELECTED lane (elect.sync -- with `lane == 0` the compiler wraps every tcgen05.mma in a
+//     register-to-uniform broadcast loop) issues the twelve tcgen05.mma of a chunk as soon as its stage is full, chain
+//     after chain into the FOUR 128-column TMEM accumulators, and hands the slots back through tcgen05.commit;
 //   * warps 0-3 and 4-7 (two "solver" groups, thread = TMEM lane = row of S, 192 registers after setmaxnreg): take
-//     the CTA's rows alternately; fold the row's chains into registers as they complete (freeing the accumulator),
-//     then run CG with a 128-thread named barrier.  While one group iterates, the other folds / iterates on the next
-//     row and the gather + MMA warps are several rows ahead, so the tensor pipe no longer waits for anything but data.
-// Rows are assigned to CTAs on the host (cymf_als_ws_schedule_host: longest-processing-time-first over nnz + a per-row
-// constant), so every role walks the same static list and no role ever has to tell another what comes next: all
-// hand-overs are mbarrier phases whose parity follows from counters each role keeps for itself.
+//     the CTA's rows alternately; each group owns two accumulators and two sum-y~ slots (so that every mbarrier has ONE
+//     waiter that sees each of its phases: a waiter that skipped a use would read the parity of the wrong phase); fold
+//     the row's chains into registers as they complete (freeing the accumulator), then run CG (Chronopoulos-Gear form:
+//     one reduction round per iteration) with a 128-thread named barrier.  While one group iterates, the other folds /
+//     iterates on the next row and the copy / convert / MMA warps are several rows ahead.
+// Rows are assigned to CTAs on the host (cymf_als_ws_schedule_host: longest rows first to the least loaded CTA; inside
+// a CTA's list long and short rows alternate), so every role walks the same static list and no role ever has to tell
+// another what comes next: all hand-overs are mbarrier phases whose parity follows from counters each role keeps for
+// itself.  A hand-over that does not complete within ~2 s is recorded in `debug` and the kernel ends instead of hanging.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -33,7 +43,7 @@
 namespace cymf {
 namespace tc {
 
-constexpr int WS_THREADS = 512;       // 4 warpgroups: solver 0, solver 1, gather, mma (+3 idle warps)
+constexpr int WS_THREADS = 512;       // 4 warpgroups: solver 0, solver 1, convert, {mma, copy, copy, idle}
 constexpr int WS_NHI = 10;            // raw / hi operand slots (16 KB each): chunk t lives in slot t mod 10
 constexpr int WS_NLO = 3;             // lo operand slots (16 KB each): chunk t's lo tile lives in slot t mod 3
 constexpr int WS_NI = 2;              // copy-issuing warps (16 items of a chunk each)

@@ -408,6 +408,14 @@ class AlsSession(object):
             # Measured: ml-20m on one GPU has no such row (19.4 ms/epoch either way, 22.2 ms with a floor of 4096);
             # sharded over 8 GPUs the same rows are 8x larger relative to their block and do qualify.
             floor = max(self.heavy_min, int(lengths.sum()) // self.tail_divisor)
+            if self.row_solver == "tc" and self.use_ws and "CYMF_ALS_TAIL_DIVISOR" not in os.environ:
+                # With the warp-specialised solver a long row costs its CTA ~25 ns per entry (1600 cycles per 32-entry
+                # chunk) and only delays the half sweep by what exceeds the CTA's fair share, while the direct path
+                # costs ~0.9 ms per half sweep as soon as ONE row takes it (slab Gram + f64 LDL^T + stream join).
+                # Measured, ml-20m shape on 4 GPUs (tools/als_tail_ab.py): 4.52 ms/epoch with 6 direct rows per rank,
+                # 4.36 with 1, 3.44 with none (the 31 k-entry row then runs 0.8 ms in one CTA).  So: direct solve only
+                # for a row that exceeds its CTA's fair share by more than ~1 ms = 40 k entries.
+                floor = max(self.heavy_min, int(lengths.sum()) // int(self._L.cymf_als_ws_ctas()) + 40_000)
             while True:                                        # keep the slab workspace under 8 GB
                 nh = int((lengths >= floor).sum())             # a prefix: lengths are sorted in decreasing order
                 slabs = int(((lengths[:nh] + 511) // 512).sum())

@@ -223,10 +223,13 @@ def test_evaluator_hook_and_early_stopping():
 
 
 @pytest.mark.parametrize("K", [32, 64, 128])
-def test_heavy_rows_direct_solve(oracle, K):
+def test_heavy_rows_direct_solve(oracle, K, monkeypatch):
     """Rows of >= heavy_min entries take the direct path (gathered tcgen05 Gram per 512-entry slab + f64 LDL^T solve,
-    cymf_als_heavy_rows_dev) instead of CG: same factors as the reference's dgesv solves, and as the CG path."""
+    cymf_als_heavy_rows_dev) instead of CG: same factors as the reference's dgesv solves, and as the CG path.
+    (The tail divisor is set explicitly: by default the warp-specialised solver keeps every row that does not exceed
+    its CTA's fair share by 40 k entries, which no row of this small matrix does.)"""
     import cymf_b200 as cymf
+    monkeypatch.setenv("CYMF_ALS_TAIL_DIVISOR", "256")
     X = cymf.synth.synth_implicit(900, 700, 60000, seed=12).tolil()
     X[3, :] = 1                                               # a row with every item: 700 entries = 2 slabs
     X[:, 5] = 1                                               # and a column with every user: 900 entries
