@@ -224,3 +224,49 @@ def test_synthetic_movielens_has_the_reference_dataset_shape():
         cymf.dataset.SyntheticMovieLens("ml-9000")
     with pytest.raises(RuntimeError):
         cymf.dataset.MovieLens("ml-100k")
+
+
+@pytest.mark.parametrize("n,n_ctas,seed", [(0, 4, 0), (1, 4, 1), (5, 8, 2), (1000, 7, 3), (20000, 148, 4)])
+def test_ws_row_schedule_is_a_balanced_permutation(n, n_ctas, seed):
+    """cymf_als_ws_schedule_host (host-only): every row lands in exactly one CTA's list with its extent, the loads
+    (entries + row_cost per row) differ by about one row, a row far above the mean gets a CTA (almost) to itself, and
+    inside a list long and short rows alternate (longest, shortest, second longest, ...)."""
+    import ctypes as C
+    from cymf_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(seed)
+    lens = np.clip(np.rint(rng.lognormal(0.0, 1.2, n) * 150), 0, None).astype(np.int64)
+    if n >= 1000:
+        lens[rng.integers(0, n)] = 40 * int(lens.sum() // n_ctas // 10 + 1)          # one very long row (~4x the mean load)
+    indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    rows = rng.permutation(n).astype(np.int32)                                       # any row order
+    cta_ptr = np.full(n_ctas + 1, -1, np.int32)
+    rowinfo = np.full(max(4 * n, 1), -1, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    assert L.cymf_als_ws_schedule_host(p(indptr), p(rows), n, n_ctas, 256, p(cta_ptr), p(rowinfo)) == 0
+    assert cta_ptr[0] == 0 and cta_ptr[-1] == n and (np.diff(cta_ptr) >= 0).all()
+    ri = rowinfo[:4 * n].reshape(n, 4)
+    assert np.array_equal(np.sort(ri[:, 0]), np.arange(n))                            # a permutation of the rows
+    assert np.array_equal(ri[:, 1], lens[ri[:, 0]])                                   # nnz
+    lo = ri[:, 2].astype(np.uint32).astype(np.int64) | (ri[:, 3].astype(np.int64) << 32)
+    assert np.array_equal(lo, indptr[ri[:, 0]])                                       # 64-bit row start, two words
+    if n == 0:
+        return
+    loads = np.array([int((ri[cta_ptr[b]:cta_ptr[b + 1], 1] + 256).sum()) for b in range(n_ctas)])
+    mean = loads.sum() / n_ctas
+    big = int(lens.max()) + 256
+    if n < n_ctas:                                                                   # fewer rows than CTAs: one row each
+        assert (np.diff(cta_ptr) <= 1).all()
+    elif big <= mean:
+        assert loads.max() - loads.min() <= 2 * big
+    else:                                                                            # the long row's CTA holds (nearly) only it
+        assert loads.max() <= big + 2 * (int(np.sort(lens)[-2]) + 256)
+        others = np.delete(loads, loads.argmax())
+        assert others.max() - others.min() <= 2 * (int(np.sort(lens)[-2]) + 256)
+    for b in range(n_ctas):                                                           # longest, shortest, 2nd longest, ...
+        seg = ri[cta_ptr[b]:cta_ptr[b + 1], 1]
+        if seg.shape[0] >= 4:
+            assert (np.diff(seg[0::2]) <= 0).all() and (np.diff(seg[1::2]) >= 0).all()
+            assert seg[0] == seg.max() and seg[1] == seg.min()
+    with pytest.raises(_lib.CymfError):
+        _lib.check(L.cymf_als_ws_schedule_host(p(indptr), p(rows), n, 0, 256, p(cta_ptr), p(rowinfo)))
