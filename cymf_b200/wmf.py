@@ -1,6 +1,7 @@
 """`cymf.WMF` on B200s: same constructor / `fit` / `_als` signatures and attributes as the reference class
 (cymf/wmf.pyx:32-174); the Gram product and the prange row loop of `_als` (wmf.pyx:142-174) run as CUDA kernels
-(cymf_b200/csrc/als.cu) reached through the C ABI of include/cymf_b200.h.
+(cymf_b200/csrc/: als_ws.cu -- warp-specialised tensor-core row solver --, als_dual.cu -- short rows in their dual
+form --, als_tc.cu, als.cu, tc_gemm*.cu) reached through the C ABI of include/cymf_b200.h.
 
 Host logic kept in Python as in the reference: input coercion and seeded init (wmf.pyx:69-92), the epoch loop
 with per-epoch validation / early stopping (wmf.pyx:110-132).  The reference re-transposes X twice per epoch
@@ -8,12 +9,20 @@ with per-epoch validation / early stopping (wmf.pyx:110-132).  The reference re-
 
 The reference factorises a dense K x K matrix per row with LAPACK dgesv; here each row is solved by conjugate
 gradient to a relative residual `cg_tol` (default 1e-6 in float32, 1e-10 in float64), which keeps W and H
-within 1e-4 (relative) of the reference's -- see tests/test_wmf_gpu.py.
+within 1e-4 (relative) of the reference's -- see tests/test_wmf_gpu.py.  In float32 with K <= 128 the row's K x K
+matrix (wmf.pyx:161-166) is built once on the tensor cores from ONE gather of the row (rows of at most 64 entries: the
+n x n matrix of the dual system instead) and the iteration runs out of registers; float64 and K > 128 stream the row
+once per iteration (cymf_als_cg_dev).
+
+Environment switches (A/B runs, tests): CYMF_ALS_WS=0 (CTA-per-row solver instead of the warp-specialised one),
+CYMF_ALS_DUAL=0 / CYMF_ALS_DUAL_MAX, CYMF_ALS_WS_TMA=0|1 (cp.async / TMA gather), CYMF_ALS_SHORT, CYMF_ALS_ROWS=cg,
+CYMF_NO_TCGEN05=1, CYMF_ALS_TAIL_DIVISOR, CYMF_ALS_GRAPH=0, CYMF_CHOL_BLOCKED=0.
 
 Multi-GPU (one process per GPU, torch.distributed/NCCL already initialised): rows of each half sweep are
 partitioned over the ranks (heaviest-first round-robin deal, so row counts are equal and nnz is balanced), every
-rank holds a full replica of both factor matrices, solves its own block, then the blocks are all-gathered and the
-K x K Gram partials of the freshly solved blocks are all-reduced.  world_size == 1 runs the same code.
+rank holds the whole fixed side in the coordinates of its Cholesky change of variables, solves its own block, then
+writes the transformed block into every rank's copy from the GEMM epilogue (NVLink peer stores) and the K x K Gram
+partials of the freshly solved blocks are summed by peer loads.  world_size == 1 runs the same code.
 """
 import ctypes as C
 import os
